@@ -1,0 +1,106 @@
+/*
+ * msda_b200.h — C ABI of the B200-native multi-scale deformable attention operator.
+ *
+ * Drop-in boundary.  These entry points replace the two functions the upstream
+ * `MultiScaleDeformableAttention` extension exports (IDEA-Research/MaskDINO,
+ * maskdino/modeling/pixel_decoder/ops/src/vision.cpp: `ms_deform_attn_forward`,
+ * `ms_deform_attn_backward`; dispatch in src/ms_deform_attn.h; host wrappers in
+ * src/cuda/ms_deform_attn_cuda.cu).  That checkout is not vendored by the reference repository:
+ * it is put on sys.path at /root/reference/training/maskdino/train_full.py:15-16 and reached through
+ * `from maskdino import add_maskdino_config` (train_full.py:28) + `build_model(cfg)`
+ * (train_full.py:308, evaluate.py:109, visualize.py:251).
+ *
+ * Conventions (all entry points)
+ *   - plain pointers and sizes only; no torch / pybind types.
+ *   - every buffer is allocated, owned and kept alive by the caller; the library never allocates,
+ *     frees or synchronises.  All work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - all device buffers are contiguous, on the current CUDA device, 16-byte aligned.
+ *   - return value: 0 = success; < 0 = argument validation failure (MSDA_ERR_*); > 0 = cudaError_t
+ *     of the failing runtime call / launch.  No printf-and-continue.
+ *   - re-entrant; no global mutable state except a one-time, thread-safe kernel attribute set-up.
+ *
+ * Tensor layouts (row-major, identical to upstream)
+ *   value              (N, S, M, D)          value dtype          S = sum_l H_l*W_l
+ *   spatial_shapes     (L, 2)  int64         rows are (H_l, W_l)      [device memory]
+ *   level_start_index  (L,)    int64         prefix sums of H_l*W_l   [device memory]
+ *   sampling_loc       (N, Lq, M, L, P, 2)   float32 (float64 when value is float64); last dim (x, y)
+ *   attn_weight        (N, Lq, M, L, P)      same dtype as sampling_loc
+ *   output             (N, Lq, M*D)          value dtype
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* value dtype codes */
+enum { MSDA_F32 = 0, MSDA_F64 = 1, MSDA_BF16 = 2, MSDA_F16 = 3 };
+
+/* validation errors (negative so they never collide with cudaError_t) */
+enum {
+  MSDA_OK = 0,
+  MSDA_ERR_NULL_POINTER = -1,
+  MSDA_ERR_BAD_SHAPE = -2,       /* a dimension is <= 0 or too large (L > 32, overflow of 2^31 pairs) */
+  MSDA_ERR_BAD_DTYPE = -3,
+  MSDA_ERR_MISALIGNED = -4,      /* a buffer is not 16-byte aligned */
+  MSDA_ERR_IM2COL_STEP = -5,     /* N % min(N, im2col_step) != 0 (upstream assert kept) */
+  MSDA_ERR_SCRATCH_TOO_SMALL = -6
+};
+
+/* backward flags */
+enum {
+  MSDA_BWD_DEFAULT = 0,
+  /* 16-bit value dtypes only: scatter grad_value with packed 16-bit red.global.add straight into
+   * grad_value instead of fp32 atomics into `scratch` followed by one rounding pass.  Faster, less
+   * accurate (every atomic rounds to 8/11 mantissa bits), order-nondeterministic. */
+  MSDA_BWD_GRAD_VALUE_16BIT_ATOMICS = 1
+};
+
+/* Library ABI version (bumped on any signature change). */
+int msda_abi_version(void);
+
+/* Human-readable text for a return code of this library (static storage). */
+const char* msda_error_string(int code);
+
+/*
+ * Forward.  Replaces upstream `ms_deform_attn_forward(value, spatial_shapes, level_start_index,
+ * sampling_loc, attn_weight, im2col_step) -> output` (vision.cpp / ms_deform_attn_cuda.cu
+ * `ms_deform_attn_cuda_forward`).  `output` is fully overwritten.  `im2col_step` is validated the
+ * way upstream does (N % min(N, im2col_step) == 0) and otherwise ignored: one launch covers the
+ * whole batch, which is semantically identical to upstream's per-chunk loop.
+ */
+int msda_forward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                 const void* sampling_loc, const void* attn_weight, void* output,
+                 int N, int S, int M, int D, int Lq, int L, int P,
+                 int value_dtype, int im2col_step, void* stream);
+
+/* Bytes of zero-initialisable scratch `msda_backward` needs for this problem (0 if none). */
+size_t msda_backward_scratch_bytes(int N, int S, int M, int D, int value_dtype, int flags);
+
+/*
+ * Backward.  Replaces upstream `ms_deform_attn_backward(value, spatial_shapes, level_start_index,
+ * sampling_loc, attn_weight, grad_output, im2col_step) -> [grad_value, grad_sampling_loc,
+ * grad_attn_weight]` (`ms_deform_attn_cuda_backward`).  grad_output is (N, Lq, M*D) in the value
+ * dtype.  grad_sampling_loc and grad_attn_weight are fully overwritten (no pre-zeroing needed).
+ * grad_value is zeroed by this call (cudaMemsetAsync on `stream`) before accumulation, as is
+ * `scratch` (fp32 accumulation buffer of msda_backward_scratch_bytes(), may be NULL when 0).
+ */
+int msda_backward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                  const void* sampling_loc, const void* attn_weight, const void* grad_output,
+                  void* grad_value, void* grad_sampling_loc, void* grad_attn_weight,
+                  void* scratch, size_t scratch_bytes,
+                  int N, int S, int M, int D, int Lq, int L, int P,
+                  int value_dtype, int im2col_step, int flags, void* stream);
+
+/* Number of kernel launches (not memsets) the last forward/backward call on this thread enqueued;
+ * used by bench.py to report `gpu_launches`. */
+int msda_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

@@ -1,0 +1,112 @@
+"""GPU: the MSDeformAttn nn.Module (encoder and decoder call patterns) against the same module arithmetic on
+the CPU with the oracle core in place of the CUDA function."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ms_deform_attn_core_pytorch
+from tests.helpers import lsi_of, rel_to_max
+
+pytestmark = pytest.mark.gpu
+
+
+def reference_module_forward(m, query, reference_points, input_flatten, ss, padding_mask=None):
+    """Upstream MSDeformAttn.forward arithmetic, restated with the oracle core (CPU, module's dtype)."""
+    N, Lq, _ = query.shape
+    _, S, _ = input_flatten.shape
+    value = F.linear(input_flatten, m.value_proj.weight, m.value_proj.bias)
+    if padding_mask is not None:
+        value = value.masked_fill(padding_mask[..., None], 0.0)
+    value = value.view(N, S, m.n_heads, m.d_model // m.n_heads)
+    off = F.linear(query, m.sampling_offsets.weight, m.sampling_offsets.bias).view(N, Lq, m.n_heads, m.n_levels, m.n_points, 2)
+    aw = F.linear(query, m.attention_weights.weight, m.attention_weights.bias).view(N, Lq, m.n_heads, m.n_levels * m.n_points)
+    aw = aw.softmax(-1).view(N, Lq, m.n_heads, m.n_levels, m.n_points)
+    if reference_points.shape[-1] == 2:
+        norm = torch.stack([ss[..., 1], ss[..., 0]], -1)
+        loc = reference_points[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+    else:
+        loc = reference_points[:, :, None, :, None, :2] + off / m.n_points * reference_points[:, :, None, :, None, 2:] * 0.5
+    out = ms_deform_attn_core_pytorch(value, ss, loc, aw)
+    return F.linear(out, m.output_proj.weight, m.output_proj.bias)
+
+
+@pytest.fixture(scope="module")
+def ops(built_library):
+    assert torch.cuda.is_available()
+    import vision_instance_seg_b200 as pkg
+    return pkg
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("with_mask", [False, True])
+def test_module_forward_backward_matches_cpu_restatement(ops, ref_dim, with_mask):
+    from vision_instance_seg_b200 import workloads as W
+    torch.manual_seed(ref_dim * 10 + with_mask)
+    shapes = [(12, 10), (6, 5), (3, 3)]
+    ss = W.make_spatial_shapes(shapes)
+    lsi = W.make_level_start_index(ss)
+    S = int(ss.prod(1).sum())
+    N = 2
+    m_cpu = ops.MSDeformAttn(d_model=64, n_levels=3, n_heads=4, n_points=4).double()
+    with torch.no_grad():   # make the zero-initialised projections non-trivial
+        m_cpu.sampling_offsets.weight.normal_(0, 0.05)
+        m_cpu.attention_weights.weight.normal_(0, 0.5)
+        m_cpu.attention_weights.bias.normal_(0, 0.5)
+    m_gpu = ops.MSDeformAttn(d_model=64, n_levels=3, n_heads=4, n_points=4).double()
+    m_gpu.load_state_dict(m_cpu.state_dict())
+    m_gpu = m_gpu.cuda()
+    src = torch.randn(N, S, 64, dtype=torch.float64)
+    if ref_dim == 2:
+        Lq = S
+        query = src + 0.1 * torch.randn(N, S, 64, dtype=torch.float64)
+        ref = W.get_reference_points(ss, torch.ones(N, 3, 2)).double()
+    else:
+        Lq = 13
+        query = torch.randn(N, Lq, 64, dtype=torch.float64)
+        ref = torch.cat([torch.rand(N, Lq, 1, 2, dtype=torch.float64).expand(-1, -1, 3, -1),
+                         torch.rand(N, Lq, 1, 2, dtype=torch.float64).expand(-1, -1, 3, -1) * 0.4 + 0.05], -1)
+    mask = None
+    if with_mask:
+        mask = torch.zeros(N, S, dtype=torch.bool)
+        mask[0, ::7] = True
+        mask[1, -20:] = True
+    q_c = query.clone().requires_grad_(True)
+    s_c = src.clone().requires_grad_(True)
+    out_c = reference_module_forward(m_cpu, q_c, ref, s_c, ss, mask)
+    g = torch.randn_like(out_c)
+    out_c.backward(g)
+    q_g = query.cuda().requires_grad_(True)
+    s_g = src.cuda().requires_grad_(True)
+    out_g = m_gpu(q_g, ref.cuda(), s_g, ss.cuda(), lsi.cuda(), mask.cuda() if mask is not None else None)
+    out_g.backward(g.cuda())
+    assert rel_to_max(out_g, out_c) < 1e-10
+    assert rel_to_max(q_g.grad, q_c.grad) < 1e-9
+    assert rel_to_max(s_g.grad, s_c.grad) < 1e-9
+    for (n, p_g), (_, p_c) in zip(m_gpu.named_parameters(), m_cpu.named_parameters()):
+        assert rel_to_max(p_g.grad, p_c.grad) < 1e-9, n
+
+
+def test_module_fp32_default_shape_and_autocast_bf16(ops):
+    """d_model 256 / 8 heads / 4 levels / 4 points in fp32, and under torch.autocast(bfloat16) where the value
+    projection arrives as bf16 while locations / weights are computed from bf16 Linears."""
+    from vision_instance_seg_b200 import workloads as W
+    torch.manual_seed(0)
+    shapes = [(16, 16), (8, 8), (4, 4), (2, 2)]
+    ss = W.make_spatial_shapes(shapes)
+    lsi = W.make_level_start_index(ss)
+    S = int(ss.prod(1).sum())
+    m = ops.MSDeformAttn().cuda()
+    with torch.no_grad():
+        m.sampling_offsets.weight.normal_(0, 0.02)
+        m.attention_weights.weight.normal_(0, 0.2)
+    src = torch.randn(2, S, 256)
+    ref = W.get_reference_points(ss, torch.ones(2, 4, 2))
+    out = m(src.cuda(), ref.cuda(), src.cuda(), ss.cuda(), lsi.cuda())
+    m_cpu = ops.MSDeformAttn()
+    m_cpu.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()})
+    want = reference_module_forward(m_cpu, src, ref, src, ss)
+    assert rel_to_max(out, want) < 1e-4           # includes four fp32 GEMMs (TF32 off by default for matmul)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out_bf = m(src.cuda(), ref.cuda(), src.cuda(), ss.cuda(), lsi.cuda())
+    assert out_bf.dtype == torch.bfloat16
+    assert rel_to_max(out_bf, want) < 5e-2

@@ -1,0 +1,70 @@
+"""Quick GPU development check: parity at small shapes + timing at cfg3.  Not a test, not the bench."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import vision_instance_seg_b200 as pkg
+from vision_instance_seg_b200 import MSDeformAttnFunction, workloads as W, MultiScaleDeformableAttention as MSDA
+from oracle import ms_deform_attn_oracle_grads
+
+dev = "cuda"
+
+def relerr(got, want):
+    want = want.double().cpu(); got = got.detach().double().cpu()
+    return ((got - want).abs().max() / want.abs().max().clamp_min(1e-30)).item()
+
+def parity(name, maker, dtype, flags=0, **kw):
+    MSDA.backward_flags = flags
+    v, ss, lsi, loc, attn = maker(dtype=dtype, device=dev, **kw)
+    v.requires_grad_(True); loc.requires_grad_(True); attn.requires_grad_(True)
+    out = MSDeformAttnFunction.apply(v, ss, lsi, loc, attn, 128)
+    go = torch.randn_like(out)
+    out.backward(go)
+    torch.cuda.synchronize()
+    ref = ms_deform_attn_oracle_grads(v.detach().float(), ss.cpu(), loc.detach(), attn.detach(), go.float())
+    r = dict(case=name, dtype=str(dtype), flags=flags, out=relerr(out, ref[0]), gv=relerr(v.grad, ref[1]),
+             gl=relerr(loc.grad, ref[2]), ga=relerr(attn.grad, ref[3]))
+    print(json.dumps(r), flush=True)
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+def timing(name, maker, dtype, flags=0, **kw):
+    MSDA.backward_flags = flags
+    v, ss, lsi, loc, attn = maker(dtype=dtype, device=dev, **kw)
+    N, S, M, D = v.shape; Lq = loc.shape[1]; L, P = loc.shape[3], loc.shape[4]
+    go = torch.randn(N, Lq, M * D, device=dev, dtype=dtype)
+    t_f = timeit(lambda: MSDA.ms_deform_attn_forward(v, ss, lsi, loc, attn, 128))
+    t_b = timeit(lambda: MSDA.ms_deform_attn_backward(v, ss, lsi, loc, attn, go, 128))
+    ab = W.algorithmic_bytes(N, S, Lq, M, D, L, P, v.element_size())
+    print(json.dumps(dict(case=name, dtype=str(dtype), flags=flags, fwd_ms=t_f, bwd_ms=t_b, points=ab["points"],
+                          fwd_GBps=ab["fwd"] / t_f / 1e6, bwd_GBps=ab["bwd"] / t_b / 1e6,
+                          fwdbwd_Gpts=ab["points"] / (t_f + t_b) / 1e6)), flush=True)
+
+if __name__ == "__main__":
+    small = [(16, 16), (8, 8), (4, 4)]
+    c1 = W.CONFIGS["cfg1_512_fp32"]["shapes"]; c3 = W.CONFIGS["cfg3_swinl_1024_bf16"]["shapes"]
+    parity("small_enc", W.make_encoder_inputs, torch.float32, shapes=small, batch=2)
+    parity("small_uni", W.make_uniform_inputs, torch.float32, shapes=small, batch=2)
+    parity("small_uni64", W.make_uniform_inputs, torch.float64, shapes=small, batch=2)
+    parity("cfg1_enc", W.make_encoder_inputs, torch.float32, shapes=c1, batch=2)
+    parity("cfg1_enc", W.make_encoder_inputs, torch.bfloat16, shapes=c1, batch=2)
+    parity("cfg1_enc", W.make_encoder_inputs, torch.bfloat16, flags=1, shapes=c1, batch=2)
+    parity("cfg1_enc", W.make_encoder_inputs, torch.float16, shapes=c1, batch=2)
+    parity("cfg1_uni_d30", W.make_uniform_inputs, torch.float32, shapes=small, batch=2, head_dim=30)
+    parity("cfg1_uni_d64", W.make_uniform_inputs, torch.float32, shapes=small, batch=2, head_dim=64)
+    parity("cfg1_dec", W.make_decoder_inputs, torch.bfloat16, shapes=c1, batch=2)
+    parity("cfg3_n2_enc", W.make_encoder_inputs, torch.bfloat16, shapes=c3, batch=2)
+    parity("cfg3_n2_enc", W.make_encoder_inputs, torch.bfloat16, flags=1, shapes=c3, batch=2)
+    timing("cfg1", W.make_encoder_inputs, torch.float32, shapes=c1, batch=2)
+    timing("cfg3", W.make_encoder_inputs, torch.bfloat16, shapes=c3, batch=16)
+    timing("cfg3", W.make_encoder_inputs, torch.bfloat16, flags=1, shapes=c3, batch=16)
+    timing("cfg3_fp32", W.make_encoder_inputs, torch.float32, shapes=c3, batch=16)
+    timing("cfg3_uniform", W.make_uniform_inputs, torch.bfloat16, shapes=c3, batch=16)
+    timing("cfg4_dec", W.make_decoder_inputs, torch.bfloat16, shapes=c3, batch=16)

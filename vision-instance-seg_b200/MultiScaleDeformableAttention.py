@@ -1,0 +1,116 @@
+"""Stand-in for the upstream pybind11 extension module ``MultiScaleDeformableAttention``.
+
+Upstream (IDEA-Research/MaskDINO ``maskdino/modeling/pixel_decoder/ops/src/vision.cpp``) exports
+``ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+im2col_step) -> Tensor`` and ``ms_deform_attn_backward(..., grad_output, im2col_step) -> [Tensor x3]``;
+``functions/ms_deform_attn_func.py`` imports the module as ``MSDA``.  The same two functions, with the
+same argument meaning and the same error behaviour (``RuntimeError`` for non-contiguous / non-CUDA
+tensors and for a batch that ``im2col_step`` does not divide), are provided here on top of the C ABI.
+
+Differences that are deliberate and documented in INTEGRATION.md:
+* 16-bit ``value`` (bfloat16 / float16) is accepted (upstream dispatches float / double only);
+  ``sampling_loc`` / ``attn_weight`` are consumed in float32 in that case.
+* kernel launch failures raise instead of being printf-ed and swallowed.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.MSDA_F32, torch.float64: _lib.MSDA_F64,
+           torch.bfloat16: _lib.MSDA_BF16, torch.float16: _lib.MSDA_F16}
+
+#: backward flags (see include/msda_b200.h); overridable per process with MSDA_B200_GRAD_VALUE_16BIT=1
+backward_flags = _lib.MSDA_BWD_GRAD_VALUE_16BIT_ATOMICS if os.environ.get("MSDA_B200_GRAD_VALUE_16BIT") == "1" \
+    else _lib.MSDA_BWD_DEFAULT
+
+
+def _require(t: torch.Tensor, name: str) -> None:
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} tensor has to be contiguous")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+
+
+def _aux_dtype(value: torch.Tensor) -> torch.dtype:
+    return torch.float64 if value.dtype == torch.float64 else torch.float32
+
+
+def _dims(value, spatial_shapes, sampling_loc):
+    if value.dim() != 4 or sampling_loc.dim() != 6:
+        raise RuntimeError("value must be (N, S, M, D) and sampling_loc (N, Lq, M, L, P, 2)")
+    N, S, M, D = value.shape
+    _, Lq, M2, L, P, two = sampling_loc.shape
+    if M2 != M or two != 2 or spatial_shapes.shape[0] != L or sampling_loc.shape[0] != N:
+        raise RuntimeError("inconsistent shapes between value, spatial_shapes and sampling_loc")
+    return N, S, M, D, Lq, L, P
+
+
+def _meta(t: torch.Tensor, device) -> torch.Tensor:
+    if t.dtype != torch.int64 or t.device != device or not t.is_contiguous():
+        t = t.to(device=device, dtype=torch.int64).contiguous()
+    return t
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+    for t, n in ((value, "value"), (spatial_shapes, "spatial_shapes"), (level_start_index, "level_start_index"),
+                 (sampling_loc, "sampling_loc"), (attn_weight, "attn_weight")):
+        _require(t, n)
+    if value.dtype not in _DTYPES:
+        raise RuntimeError(f"ms_deform_attn_forward not implemented for '{value.dtype}'")
+    N, S, M, D, Lq, L, P = _dims(value, spatial_shapes, sampling_loc)
+    aux = _aux_dtype(value)
+    loc = sampling_loc if sampling_loc.dtype == aux else sampling_loc.to(aux)
+    attn = attn_weight if attn_weight.dtype == aux else attn_weight.to(aux)
+    shapes = _meta(spatial_shapes, value.device)
+    lsi = _meta(level_start_index, value.device)
+    lib = _lib.load_library()
+    with torch.cuda.device(value.device):
+        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        if out.numel() == 0:
+            return out
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = lib.msda_forward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), loc.data_ptr(), attn.data_ptr(),
+                              out.data_ptr(), N, S, M, D, Lq, L, P, _DTYPES[value.dtype], int(im2col_step), stream)
+    _lib.check(rc, "ms_deform_attn_forward")
+    return out
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                            im2col_step):
+    for t, n in ((value, "value"), (spatial_shapes, "spatial_shapes"), (level_start_index, "level_start_index"),
+                 (sampling_loc, "sampling_loc"), (attn_weight, "attn_weight"), (grad_output, "grad_output")):
+        _require(t, n)
+    if value.dtype not in _DTYPES:
+        raise RuntimeError(f"ms_deform_attn_backward not implemented for '{value.dtype}'")
+    N, S, M, D, Lq, L, P = _dims(value, spatial_shapes, sampling_loc)
+    aux = _aux_dtype(value)
+    loc = sampling_loc if sampling_loc.dtype == aux else sampling_loc.to(aux)
+    attn = attn_weight if attn_weight.dtype == aux else attn_weight.to(aux)
+    go = grad_output if grad_output.dtype == value.dtype else grad_output.to(value.dtype)
+    shapes = _meta(spatial_shapes, value.device)
+    lsi = _meta(level_start_index, value.device)
+    lib = _lib.load_library()
+    code = _DTYPES[value.dtype]
+    with torch.cuda.device(value.device):
+        grad_value = torch.empty_like(value)
+        grad_loc = torch.empty(sampling_loc.shape, dtype=aux, device=value.device)
+        grad_attn = torch.empty(attn_weight.shape, dtype=aux, device=value.device)
+        if grad_loc.numel() == 0 or value.numel() == 0:
+            return [grad_value.zero_(), grad_loc.zero_(), grad_attn.zero_()]
+        nbytes = lib.msda_backward_scratch_bytes(N, S, M, D, code, backward_flags)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=value.device) if nbytes else None
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = lib.msda_backward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), loc.data_ptr(), attn.data_ptr(),
+                               go.data_ptr(), grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(),
+                               scratch.data_ptr() if scratch is not None else None, nbytes,
+                               N, S, M, D, Lq, L, P, code, int(im2col_step), backward_flags, stream)
+    _lib.check(rc, "ms_deform_attn_backward")
+    if grad_loc.dtype != sampling_loc.dtype:
+        grad_loc = grad_loc.to(sampling_loc.dtype)
+    if grad_attn.dtype != attn_weight.dtype:
+        grad_attn = grad_attn.to(attn_weight.dtype)
+    return [grad_value, grad_loc, grad_attn]

@@ -1,0 +1,24 @@
+"""B200-native multi-scale deformable attention (the MSDeformAttn hot path of the Swin/R50 +
+Mask2Former/MaskDINO stack driven by Wlsghdh/VISION-Instance-Seg's training scripts).
+
+Import name: ``vision_instance_seg_b200`` (the repo-root shim maps it onto this directory).
+
+Public surface — identical to the upstream ``maskdino/modeling/pixel_decoder/ops`` package that the
+reference reaches through ``build_model(cfg)`` (/root/reference/training/maskdino/train_full.py:308):
+
+* ``MSDeformAttnFunction.apply(value, spatial_shapes, level_start_index, sampling_locations,
+  attention_weights, im2col_step)``
+* ``MSDeformAttn(d_model=256, n_levels=4, n_heads=8, n_points=4)``
+* ``MultiScaleDeformableAttention.ms_deform_attn_forward / ms_deform_attn_backward`` (the upstream
+  extension module's two functions)
+
+All compute runs in hand-written sm_100a CUDA kernels behind the C ABI of ``include/msda_b200.h``
+(``libmsda_b200.so``).  There is no CPU path: importing works anywhere, calling the operator without
+the built library or without a CUDA device raises.
+"""
+from . import MultiScaleDeformableAttention  # noqa: F401
+from ._lib import library_path, load_library  # noqa: F401
+from .functions import MSDeformAttnFunction  # noqa: F401
+from .modules import MSDeformAttn  # noqa: F401
+
+__all__ = ["MSDeformAttn", "MSDeformAttnFunction", "MultiScaleDeformableAttention", "load_library", "library_path"]

@@ -1,0 +1,74 @@
+"""ctypes binding of the C ABI declared in include/msda_b200.h (libmsda_b200.so).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  Loading is lazy so that
+``import vision_instance_seg_b200`` works on a machine without the built library; any *use* of the
+operator without it raises ``RuntimeError`` — there is deliberately no fallback implementation.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_NAME = "libmsda_b200.so"
+_lock = threading.Lock()
+_lib = None
+
+MSDA_F32, MSDA_F64, MSDA_BF16, MSDA_F16 = 0, 1, 2, 3
+MSDA_BWD_DEFAULT = 0
+MSDA_BWD_GRAD_VALUE_16BIT_ATOMICS = 1
+
+#: every symbol include/msda_b200.h declares (tests check that the built library exports all of them)
+EXPORTED_SYMBOLS = (
+    "msda_abi_version",
+    "msda_error_string",
+    "msda_forward",
+    "msda_backward_scratch_bytes",
+    "msda_backward",
+    "msda_last_launch_count",
+)
+
+
+def library_path() -> str:
+    return os.environ.get("MSDA_B200_LIBRARY", os.path.join(_HERE, _LIB_NAME))
+
+
+def _declare(lib):
+    vp, i64p, i, sz = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    lib.msda_abi_version.restype = i
+    lib.msda_abi_version.argtypes = []
+    lib.msda_error_string.restype = ctypes.c_char_p
+    lib.msda_error_string.argtypes = [i]
+    lib.msda_last_launch_count.restype = i
+    lib.msda_last_launch_count.argtypes = []
+    lib.msda_forward.restype = i
+    lib.msda_forward.argtypes = [vp, i64p, i64p, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]
+    lib.msda_backward_scratch_bytes.restype = sz
+    lib.msda_backward_scratch_bytes.argtypes = [i, i, i, i, i, i]
+    lib.msda_backward.restype = i
+    lib.msda_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, vp, vp, vp, vp, sz,
+                                  i, i, i, i, i, i, i, i, i, i, vp]
+    return lib
+
+
+def load_library():
+    """Load (once) and return the ctypes handle of libmsda_b200.so; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            path = library_path()
+            if not os.path.exists(path):
+                raise RuntimeError(
+                    f"{_LIB_NAME} not found at {path}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(nvcc, sm_100a). This operator has no CPU or PyTorch fallback.")
+            _lib = _declare(ctypes.CDLL(path))
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_library().msda_error_string(rc).decode()
+        raise RuntimeError(f"{what} failed: {msg} (code {rc})")
