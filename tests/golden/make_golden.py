@@ -70,7 +70,7 @@ def main():
     shapes = [(4, 8), (2, 4)]
     S = sum(h * w for h, w in shapes)
     value = torch.randn(1, S, 2, 16, generator=g, dtype=f64)
-    specials = torch.tensor([0.0, 1.0, 0.5, 0.125, 0.25, 1.0 / 16, 15.0 / 16, -1.0 / 16 + 1e-9, -1.0 / 16 - 1e-3, 1.0 + 1.0 / 16 - 1e-9,
+    specials = torch.tensor([0.0, 1.0, 0.5, 0.125, 0.25, 1.0 / 16, 15.0 / 16, -1.0 / 16 + 1e-4, -1.0 / 16 - 1e-3, 1.0 + 1.0 / 16 - 1e-4,
                              1.0 + 1.0 / 8, -0.3, 1.4, 0.999999, 1e-7, 0.75], dtype=f64)
     idx = torch.randint(0, len(specials), (1, 24, 2, 2, 3, 2), generator=g)
     loc = specials[idx]
