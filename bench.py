@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — MSDeformAttn fwd+bwd sampled points/s and % of HBM roofline (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step = one pass of the hot path over one batch of synthetic input: the Swin-L MaskDINO pixel-decoder
+encoder shape (BASELINE.json configs[2]: 1024x1024 -> 4 levels 128/64/32/16, 21 760 queries, batch 16,
+value bf16 + sampling locations / attention weights fp32, 6 layers), i.e. 6 x (forward + backward) of
+MSDeformAttnFunction.  N > 1 (torchrun): every rank runs the same per-GPU batch (weak scaling, no data-path
+collective) and all-reduces one encoder-sized gradient bucket per step over NCCL on a side stream.
+
+`value`  : device-resident inputs, public autograd API, CUDA events, max over ranks.
+`e2e`    : same API, inputs start in pinned HOST memory and results end there, copies inside the timed region.
+`roofline`: dominant kernel (backward), algorithmic bytes / event-timed launch duration / measured HBM peak.
+`cpu_baseline` and `--impl reference`: the CPU oracle (restated ms_deform_attn_core_pytorch) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "msdeformattn_fwd_bwd_sampled_points_per_sec"
+UNIT = "points/s"
+WORKLOAD = "cfg3_swinl_1024_bf16"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--layers", type=int, default=None)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------------
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic_bytes(kernel_key):
+    """dram read+write bytes per launch of the dominant kernel from the committed ncu summary, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                clk, mx = float(parts[0]), float(parts[1])
+            except ValueError:
+                continue
+            smax = mx
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:   # region shorter than one sample: fall back to everything sampled
+            sm = [float(l.split(",")[0]) for _, l in self.lines if l and l.split(",")[0].strip().replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_step_time(cfg, batch, steps, warmup):
+    """Times the CPU oracle (torch restatement of ms_deform_attn_core_pytorch, fp32, all host threads) on one
+    layer's forward+backward of `batch` images of the workload.  Returns (seconds per step, points per step)."""
+    import torch
+    from oracle import ms_deform_attn_core_pytorch
+    from vision_instance_seg_b200 import workloads as W
+    torch.set_num_threads(os.cpu_count() or 1)
+    v, ss, lsi, loc, attn = W.make_encoder_inputs(cfg["shapes"], batch, torch.float32, device="cpu", seed=4321)
+    go = torch.randn(batch, loc.shape[1], v.shape[2] * v.shape[3])
+    v.requires_grad_(True), loc.requires_grad_(True), attn.requires_grad_(True)
+    pts = loc.numel() // 2
+
+    def step():
+        out = ms_deform_attn_core_pytorch(v, ss, loc, attn)
+        torch.autograd.grad(out, (v, loc, attn), go)
+
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    return times, pts
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path (oracle port), host cores only
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    from vision_instance_seg_b200 import workloads as W
+    cfg = W.CONFIGS[args.workload]
+    batch = args.cpu_sample_batch
+    times, pts = cpu_oracle_step_time(cfg, batch, args.steps, args.warmup)
+    total = sum(times)
+    value = pts * len(times) / total
+    cores = os.cpu_count() or 1
+    sample = (f"{args.workload}: {batch} image(s) x 1 layer forward+backward per step, fp32, "
+              f"ms_deform_attn_core_pytorch restatement (oracle/), torch CPU {cores} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "sample": sample, "l2_policy": "cpu run"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import vision_instance_seg_b200 as pkg
+    from vision_instance_seg_b200 import MSDeformAttnFunction, _lib, distributed as D, workloads as W
+
+    rank, local_rank, world = D.init_process_group()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = pkg.load_library()          # raises if the CUDA library is missing: no fallback
+
+    cfg = W.CONFIGS[args.workload]
+    batch = args.batch or cfg["batch"]
+    layers = args.layers or cfg.get("layers", 1)
+    dtype = cfg["dtype"]
+    maker = W.make_decoder_inputs if cfg["kind"] == "decoder" else W.make_encoder_inputs
+    extra = {"queries": cfg["queries"]} if cfg["kind"] == "decoder" else {}
+
+    # one independent input set per layer: 6 x 0.89 GB at cfg3 — far larger than the 126 MB L2, so no
+    # iteration finds its inputs cached
+    sets = []
+    for layer in range(layers):
+        v, ss, lsi, loc, attn = maker(cfg["shapes"], batch, dtype, seed=1234 + rank + 100 * layer, device=dev, **extra)
+        go = torch.randn(batch, loc.shape[1], v.shape[2] * v.shape[3], device=dev, dtype=torch.float32).to(dtype)
+        sets.append([v.requires_grad_(True), ss, lsi, loc.requires_grad_(True), attn.requires_grad_(True), go])
+    N, S, M, Dh = sets[0][0].shape
+    Lq, L, P = sets[0][3].shape[1], sets[0][3].shape[3], sets[0][3].shape[4]
+    ab = W.algorithmic_bytes(N, S, Lq, M, Dh, L, P, sets[0][0].element_size())
+    pts_per_step = ab["points"] * layers
+
+    bucket = D.GradientBucket(device=dev) if world > 1 else None
+
+    def step():
+        for v, ss, lsi, loc, attn, go in sets:
+            out = MSDeformAttnFunction.apply(v, ss, lsi, loc, attn, 128)
+            torch.autograd.grad(out, (v, loc, attn), go)
+        if bucket is not None:
+            bucket.allreduce_async()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if bucket is not None:
+        bucket.wait()
+    barrier()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    lib.msda_profile_enable(1)
+    launches0 = lib.msda_total_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    if bucket is not None:
+        bucket.wait()
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    lib.msda_profile_enable(0)
+    launches = lib.msda_total_launch_count() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    ms_total = D.max_over_ranks(e0.elapsed_time(e1), dev)
+    ms_per_step = ms_total / args.steps
+    value = pts_per_step * world / (ms_per_step * 1e-3)
+    records = _lib.profile_collect()
+    fwd_ms = [t for t, k in records if k == 1]
+    bwd_ms = [t for t, k in records if k == 2]
+
+    # ---- end to end: pinned host -> device -> fwd+bwd -> pinned host, every layer of every step ----
+    e2e = None
+    if not args.no_e2e:
+        v, ss, lsi, loc, attn, go = sets[0]
+        host_in = [t.detach().to("cpu").pin_memory() for t in (v, loc, attn, go)]
+        dev_in = [torch.empty_like(t, device=dev) for t in host_in]
+        host_out = [torch.empty((N, Lq, M * Dh), dtype=dtype).pin_memory(), torch.empty(tuple(v.shape), dtype=dtype).pin_memory(),
+                    torch.empty(tuple(loc.shape), dtype=torch.float32).pin_memory(),
+                    torch.empty(tuple(attn.shape), dtype=torch.float32).pin_memory()]
+        h2d = sum(t.numel() * t.element_size() for t in host_in) * layers
+        d2h = sum(t.numel() * t.element_size() for t in host_out) * layers
+
+        def e2e_step():
+            for _ in range(layers):
+                for d, h in zip(dev_in, host_in):
+                    d.copy_(h, non_blocking=True)
+                dv, dl, da = (t.detach().requires_grad_(True) for t in dev_in[:3])
+                dg = dev_in[3]
+                out = MSDeformAttnFunction.apply(dv, ss, lsi, dl, da, 128)
+                gv, gl, ga = torch.autograd.grad(out, (dv, dl, da), dg)
+                for h, d in zip(host_out, (out.detach(), gv, gl, ga)):
+                    h.copy_(d, non_blocking=True)
+            if bucket is not None:
+                bucket.allreduce_async()
+
+        e2e_step()
+        if bucket is not None:
+            bucket.wait()
+        barrier()
+        e0.record()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        if bucket is not None:
+            bucket.wait()
+        e1.record()
+        barrier()
+        e2e_ms = D.max_over_ranks(e0.elapsed_time(e1), dev) / args.e2e_steps
+        e2e = {"value": pts_per_step * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": args.e2e_steps,
+               "api": "MSDeformAttnFunction.apply + torch.autograd.grad, pinned host buffers"}
+        del host_in, host_out, dev_in
+
+    if rank != 0:
+        return 0
+
+    peak, peak_src = measured_peak_gbs()
+    bwd_avg = statistics.mean(bwd_ms) if bwd_ms else None
+    fwd_avg = statistics.mean(fwd_ms) if fwd_ms else None
+    roofline = None
+    if bwd_avg:
+        achieved = ab["bwd"] / (bwd_avg * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "msda_bwd (backward gather + grad_value scatter)", "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes("backward"),
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["bwd"], "avg_launch_ms": bwd_avg,
+                    "launches_timed": len(bwd_ms),
+                    "forward": {"achieved": ab["fwd"] / (fwd_avg * 1e-3) / 1e9 if fwd_avg else None,
+                                "frac": ab["fwd"] / (fwd_avg * 1e-3) / 1e9 / peak if fwd_avg else None,
+                                "algorithmic_bytes_per_launch": ab["fwd"], "avg_launch_ms": fwd_avg,
+                                "traffic": ncu_traffic_bytes("forward")},
+                    "step_frac": (ab["fwd"] + ab["bwd"]) * layers / (ms_per_step * 1e-3) / 1e9 / peak}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        times, pts = cpu_oracle_step_time(cfg, args.cpu_sample_batch, 3, 1)
+        cores = os.cpu_count() or 1
+        cpu_baseline = {"value": pts * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{args.workload}: {args.cpu_sample_batch} image(s) x 1 layer fwd+bwd, fp32, 3 timed runs "
+                                  f"after 1 warm-up ({sum(times):.1f} s), oracle ms_deform_attn_core_pytorch restatement"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {torch.bfloat16: "bf16", torch.float32: "f32", torch.float16: "f16"}[dtype], "data": "synthetic",
+        "config": {"workload": args.workload, "per_gpu_batch": batch, "global_batch": batch * world, "layers": layers,
+                   "levels": cfg["shapes"], "queries": Lq, "heads": M, "head_dim": Dh, "points": P,
+                   "aux_dtype": "f32", "points_per_step_per_gpu": pts_per_step, "parallelism": f"dp{world}",
+                   "grad_allreduce_bytes": D.ENCODER_GRAD_ELEMENTS * 4 if world > 1 else 0,
+                   "l2_policy": f"{layers} independent input sets ({layers * (ab['fwd'] + ab['bwd']) / 1e9:.1f} GB touched per step) >> 126 MB L2; no flush needed"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: re-launch ourselves one process per GPU
+        import socket
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -100,6 +100,22 @@ int msda_backward(const void* value, const int64_t* spatial_shapes, const int64_
  * used by bench.py to report `gpu_launches`. */
 int msda_last_launch_count(void);
 
+/* Process-wide, monotonically increasing count of kernel launches enqueued by this library (all threads,
+ * including autograd's backward thread). */
+long long msda_total_launch_count(void);
+
+/*
+ * Optional per-launch timing of the dominant kernels, for bench.py's roofline leg.  While enabled
+ * (process-wide) every forward / backward call records a CUDA event pair on `stream` immediately around
+ * its main kernel (kind MSDA_KERNEL_FORWARD / MSDA_KERNEL_BACKWARD; memsets and the fp32->16-bit rounding
+ * pass are outside the pair).  msda_profile_collect() waits for the recorded events, writes up to
+ * max_records (duration in ms, kind) pairs in call order, frees them and returns how many it wrote.
+ * These two calls are the only ones in the library that create events or block the host.
+ */
+enum { MSDA_KERNEL_FORWARD = 1, MSDA_KERNEL_BACKWARD = 2 };
+int msda_profile_enable(int on);
+int msda_profile_collect(float* ms, int* kinds, int max_records);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,9 @@ EXPORTED_SYMBOLS = (
     "msda_backward_scratch_bytes",
     "msda_backward",
     "msda_last_launch_count",
+    "msda_total_launch_count",
+    "msda_profile_enable",
+    "msda_profile_collect",
 )
 
 
@@ -49,7 +52,22 @@ def _declare(lib):
     lib.msda_backward.restype = i
     lib.msda_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, vp, vp, vp, vp, sz,
                                   i, i, i, i, i, i, i, i, i, i, vp]
+    lib.msda_total_launch_count.restype = ctypes.c_longlong
+    lib.msda_total_launch_count.argtypes = []
+    lib.msda_profile_enable.restype = i
+    lib.msda_profile_enable.argtypes = [i]
+    lib.msda_profile_collect.restype = i
+    lib.msda_profile_collect.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int), i]
     return lib
+
+
+def profile_collect(max_records: int = 65536):
+    """Return [(ms, kind), ...] for every kernel timed since msda_profile_enable(1) (see include/msda_b200.h)."""
+    lib = load_library()
+    ms = (ctypes.c_float * max_records)()
+    kinds = (ctypes.c_int * max_records)()
+    n = lib.msda_profile_collect(ms, kinds, max_records)
+    return [(float(ms[k]), int(kinds[k])) for k in range(n)]
 
 
 def load_library():

@@ -16,7 +16,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <type_traits>
+#include <vector>
 
 #include "msda_common.cuh"
 #include "../../include/msda_b200.h"
@@ -432,6 +435,29 @@ msda_round_scratch_any_kernel(const float* __restrict__ src, T* __restrict__ dst
 // Host side
 // =====================================================================================================
 static thread_local int g_last_launches = 0;
+static std::atomic<long long> g_total_launches{0};
+
+// ---- optional per-launch timing of the dominant kernels (bench.py's roofline leg) --------------------
+struct ProfileRecord { cudaEvent_t start, stop; int kind; };
+// process-wide (autograd runs backward on its own thread), guarded by a mutex; off by default
+static std::atomic<bool> g_profile_on{false};
+static std::mutex g_profile_mu;
+static std::vector<ProfileRecord> g_profile;
+
+struct ScopedKernelTimer {
+  cudaStream_t st; cudaEvent_t stop = nullptr; bool on = false;
+  ScopedKernelTimer(int kind, cudaStream_t s) : st(s) {
+    if (!g_profile_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_profile_mu);
+    if (g_profile.size() >= 65536) return;
+    ProfileRecord r; r.kind = kind;
+    if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return;
+    cudaEventRecord(r.start, st);
+    stop = r.stop; on = true;
+    g_profile.push_back(r);
+  }
+  ~ScopedKernelTimer() { if (on) cudaEventRecord(stop, st); }
+};
 
 struct Problem {
   int N, S, M, D, Lq, L, P;
@@ -478,10 +504,11 @@ static int launch_fwd_vec(const Problem& pr, const void* value, const int64_t* s
   if (e != cudaSuccess) return static_cast<int>(e);
   const int per_cta = kWarps * GPW;
   const int grid = (pr.total_pairs + per_cta - 1) / per_cta;
+  ScopedKernelTimer timer(MSDA_KERNEL_FORWARD, st);
   msda_fwd_vec_kernel<T, D><<<grid, kThreads, smem, st>>>(
       static_cast<const T*>(value), shapes, lsi, static_cast<const float*>(loc), static_cast<const float*>(attn),
       static_cast<T*>(out), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs);
-  ++g_last_launches;
+  ++g_last_launches, ++g_total_launches;
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -503,7 +530,7 @@ static int launch_fwd(const Problem& pr, const void* value, const int64_t* shape
   msda_fwd_any_kernel<T><<<grid, kThreads, 0, st>>>(
       static_cast<const T*>(value), shapes, lsi, static_cast<const Aux*>(loc), static_cast<const Aux*>(attn),
       static_cast<T*>(out), pr.S, pr.M, pr.D, pr.Lq, pr.L, pr.P, pr.total_pairs);
-  ++g_last_launches;
+  ++g_last_launches, ++g_total_launches;
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -521,21 +548,23 @@ static int launch_bwd_vec(const Problem& pr, const void* value, const int64_t* s
     if (use16) {
       e = allow_smem(msda_bwd_vec_kernel<T, D, true>, smem);
       if (e != cudaSuccess) return static_cast<int>(e);
+      ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD, st);
       msda_bwd_vec_kernel<T, D, true><<<grid, kThreads, smem, st>>>(
           static_cast<const T*>(value), shapes, lsi, static_cast<const float*>(loc), static_cast<const float*>(attn),
           static_cast<const T*>(go), nullptr, static_cast<T*>(gv16), static_cast<float*>(gloc),
           static_cast<float*>(gattn), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs);
-      ++g_last_launches;
+      ++g_last_launches, ++g_total_launches;
       return static_cast<int>(cudaGetLastError());
     }
   }
   e = allow_smem(msda_bwd_vec_kernel<T, D, false>, smem);
   if (e != cudaSuccess) return static_cast<int>(e);
+  ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD, st);
   msda_bwd_vec_kernel<T, D, false><<<grid, kThreads, smem, st>>>(
       static_cast<const T*>(value), shapes, lsi, static_cast<const float*>(loc), static_cast<const float*>(attn),
       static_cast<const T*>(go), gv32, nullptr, static_cast<float*>(gloc), static_cast<float*>(gattn),
       pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs);
-  ++g_last_launches;
+  ++g_last_launches, ++g_total_launches;
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -580,7 +609,7 @@ static int launch_bwd(const Problem& pr, const void* value, const int64_t* shape
           static_cast<const T*>(go), static_cast<T*>(gv), static_cast<Aux*>(gloc), static_cast<Aux*>(gattn),
           pr.S, pr.M, pr.D, pr.Lq, pr.L, pr.P, pr.total_pairs);
     }
-    ++g_last_launches;
+    ++g_last_launches, ++g_total_launches;
     rc = static_cast<int>(cudaGetLastError());
   }
   if (rc != 0) return rc;
@@ -594,7 +623,7 @@ static int launch_bwd(const Problem& pr, const void* value, const int64_t* shape
         const int grid = static_cast<int>(std::min<size_t>((n_value + 255) / 256, 148 * 16));
         msda_round_scratch_any_kernel<T><<<grid, 256, 0, st>>>(static_cast<const float*>(scratch), static_cast<T*>(gv), n_value);
       }
-      ++g_last_launches;
+      ++g_last_launches, ++g_total_launches;
       rc = static_cast<int>(cudaGetLastError());
     }
   }
@@ -626,6 +655,28 @@ extern "C" const char* msda_error_string(int code) {
 }
 
 extern "C" int msda_last_launch_count(void) { return g_last_launches; }
+
+extern "C" long long msda_total_launch_count(void) { return g_total_launches.load(); }
+
+extern "C" int msda_profile_enable(int on) {
+  g_profile_on.store(on != 0);
+  return MSDA_OK;
+}
+
+extern "C" int msda_profile_collect(float* ms, int* kinds, int max_records) {
+  std::lock_guard<std::mutex> lk(g_profile_mu);
+  int n = 0;
+  for (auto& r : g_profile) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.stop) == cudaSuccess && cudaEventElapsedTime(&t, r.start, r.stop) == cudaSuccess &&
+        n < max_records && ms && kinds) {
+      ms[n] = t; kinds[n] = r.kind; ++n;
+    }
+    cudaEventDestroy(r.start); cudaEventDestroy(r.stop);
+  }
+  g_profile.clear();
+  return n;
+}
 
 extern "C" int msda_forward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
                             const void* sampling_loc, const void* attn_weight, void* output,
