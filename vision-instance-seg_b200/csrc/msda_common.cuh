@@ -134,4 +134,132 @@ __device__ __forceinline__ Footprint<F> make_footprint(F x, F y, int H, int W) {
   return fp;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fast fp32 footprint used by the vector kernels.
+//
+// Same arithmetic as upstream up to the corner fetch: w_im = x*W - 0.5 (mul, then sub), the (-1, W) gate,
+// lw = w_im - floor(w_im).  floor() is taken with one round-down add of 1.5*2^23 (FADD.RM, full rate)
+// instead of F2I/FRND (measured 0.5 warp-instr/clk/SM on B200, profiles/microbench_issue_r01.jsonl): for
+// |t| < 2^22 the sum lies in [2^23, 2^24) where ulp = 1, so rounding down yields floor(t) + 1.5*2^23 exactly;
+// the float floor is recovered by an exact subtraction and the integer from the mantissa bits.
+//
+// Zero padding is folded into the weights: every corner address is clamped into the level (so all four
+// loads are unconditional) and an out-of-range corner gets weight 0.  The clamped address of an invalid
+// corner is always another, valid corner of the same footprint, so non-finite values propagate exactly as
+// upstream.  (A point that fails the gate altogether reads pixel (0,0)-clamped data with weight 0.)
+// ---------------------------------------------------------------------------------------------------
+struct Taps {
+  int i00, i01, i10, i11;          // pixel indices inside the level, always in range
+  float hhm, lhm, hwm, lwm;        // hh/lh/hw/lw with the row / column validity (and the gate) folded in
+  float Tm, Bm, Lm, Rm;            // 1.0f / 0.0f validity of top / bottom row and left / right column
+};
+
+__device__ __forceinline__ void floor_split(float t, float& frac, int& i) {
+  const float r = __fadd_rd(t, 12582912.0f);
+  i = __float_as_int(r) - 0x4B400000;
+  frac = __fsub_rn(t, __fsub_rn(r, 12582912.0f));
+}
+
+__device__ __forceinline__ Taps make_taps(float x, float y, int H, int W, float Hf, float Wf) {
+  Taps t;
+  const float h_im = __fsub_rn(__fmul_rn(y, Hf), 0.5f);
+  const float w_im = __fsub_rn(__fmul_rn(x, Wf), 0.5f);
+  const bool inside = (h_im > -1.f) && (w_im > -1.f) && (h_im < Hf) && (w_im < Wf);
+  float lh, lw; int iy, ix;
+  floor_split(h_im, lh, iy);
+  floor_split(w_im, lw, ix);
+  const bool top = inside && iy >= 0, bot = inside && iy < H - 1;
+  const bool left = inside && ix >= 0, right = inside && ix < W - 1;
+  t.Tm = top ? 1.f : 0.f; t.Bm = bot ? 1.f : 0.f; t.Lm = left ? 1.f : 0.f; t.Rm = right ? 1.f : 0.f;
+  t.hhm = top ? 1.f - lh : 0.f; t.lhm = bot ? lh : 0.f;
+  t.hwm = left ? 1.f - lw : 0.f; t.lwm = right ? lw : 0.f;
+  const int yt = min(max(iy, 0), H - 1), yb = min(max(iy + 1, 0), H - 1);
+  const int xl = min(max(ix, 0), W - 1), xr = min(max(ix + 1, 0), W - 1);
+  t.i00 = yt * W + xl; t.i01 = yt * W + xr; t.i10 = yb * W + xl; t.i11 = yb * W + xr;
+  return t;
+}
+
+// ---- acc[i] += w * v[i] over the VEC elements of one 16-byte vector -----------------------------------
+// fp32 values: plain FFMA with the fp32 weight.  16-bit values: Blackwell's mixed-precision FMA
+// (PTX fma.rn.f32.bf16 / .f16 -> SASS FHFMA): the product of two 16-bit operands is exact in fp32 and the
+// accumulation is fp32, one instruction per element and no unpacking.  The operand `w` must then already be
+// a 16-bit weight (bits in the low half).
+template <typename T> struct WeightT { using type = float; };
+template <> struct WeightT<__nv_bfloat16> { using type = uint32_t; };
+template <> struct WeightT<__half> { using type = uint32_t; };
+
+template <typename T> __device__ __forceinline__ typename WeightT<T>::type make_weight(float w);
+template <> __device__ __forceinline__ float make_weight<float>(float w) { return w; }
+template <> __device__ __forceinline__ uint32_t make_weight<__nv_bfloat16>(float w) {
+  return static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(w)));
+}
+template <> __device__ __forceinline__ uint32_t make_weight<__half>(float w) {
+  return static_cast<uint32_t>(__half_as_ushort(__float2half_rn(w)));
+}
+
+__device__ __forceinline__ void fma_mixed_bf16(float& acc, uint32_t v, bool hi, uint32_t w) {
+  unsigned short lo16, hi16, w16, wdummy;
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(lo16), "=h"(hi16) : "r"(v));
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(w16), "=h"(wdummy) : "r"(w));
+  if (hi) asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(acc) : "h"(hi16), "h"(w16));
+  else    asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(acc) : "h"(lo16), "h"(w16));
+}
+__device__ __forceinline__ void fma_mixed_f16(float& acc, uint32_t v, bool hi, uint32_t w) {
+  unsigned short lo16, hi16, w16, wdummy;
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(lo16), "=h"(hi16) : "r"(v));
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(w16), "=h"(wdummy) : "r"(w));
+  if (hi) asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc) : "h"(hi16), "h"(w16));
+  else    asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc) : "h"(lo16), "h"(w16));
+}
+
+template <typename T> __device__ __forceinline__ void axpy16(float* acc, const uint4& u, typename WeightT<T>::type w);
+template <> __device__ __forceinline__ void axpy16<float>(float* acc, const uint4& u, float w) {
+  acc[0] = fmaf(w, __uint_as_float(u.x), acc[0]); acc[1] = fmaf(w, __uint_as_float(u.y), acc[1]);
+  acc[2] = fmaf(w, __uint_as_float(u.z), acc[2]); acc[3] = fmaf(w, __uint_as_float(u.w), acc[3]);
+}
+template <> __device__ __forceinline__ void axpy16<__nv_bfloat16>(float* acc, const uint4& u, uint32_t w) {
+  fma_mixed_bf16(acc[0], u.x, false, w); fma_mixed_bf16(acc[1], u.x, true, w);
+  fma_mixed_bf16(acc[2], u.y, false, w); fma_mixed_bf16(acc[3], u.y, true, w);
+  fma_mixed_bf16(acc[4], u.z, false, w); fma_mixed_bf16(acc[5], u.z, true, w);
+  fma_mixed_bf16(acc[6], u.w, false, w); fma_mixed_bf16(acc[7], u.w, true, w);
+}
+template <> __device__ __forceinline__ void axpy16<__half>(float* acc, const uint4& u, uint32_t w) {
+  fma_mixed_f16(acc[0], u.x, false, w); fma_mixed_f16(acc[1], u.x, true, w);
+  fma_mixed_f16(acc[2], u.y, false, w); fma_mixed_f16(acc[3], u.y, true, w);
+  fma_mixed_f16(acc[4], u.z, false, w); fma_mixed_f16(acc[5], u.z, true, w);
+  fma_mixed_f16(acc[6], u.w, false, w); fma_mixed_f16(acc[7], u.w, true, w);
+}
+
+// ---- dot(v, g) over one 16-byte vector, fp32 accumulate (16-bit: exact products through FHFMA) ----------
+template <typename T> __device__ __forceinline__ float dot16(const uint4& v, const uint4& g, float acc);
+template <> __device__ __forceinline__ float dot16<float>(const uint4& v, const uint4& g, float acc) {
+  acc = fmaf(__uint_as_float(v.x), __uint_as_float(g.x), acc); acc = fmaf(__uint_as_float(v.y), __uint_as_float(g.y), acc);
+  acc = fmaf(__uint_as_float(v.z), __uint_as_float(g.z), acc); acc = fmaf(__uint_as_float(v.w), __uint_as_float(g.w), acc);
+  return acc;
+}
+__device__ __forceinline__ void dot_mixed_bf16(float& acc, uint32_t v, uint32_t g) {
+  unsigned short v0, v1, g0, g1;
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(v0), "=h"(v1) : "r"(v));
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(g0), "=h"(g1) : "r"(g));
+  asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(acc) : "h"(v0), "h"(g0));
+  asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(acc) : "h"(v1), "h"(g1));
+}
+__device__ __forceinline__ void dot_mixed_f16(float& acc, uint32_t v, uint32_t g) {
+  unsigned short v0, v1, g0, g1;
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(v0), "=h"(v1) : "r"(v));
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(g0), "=h"(g1) : "r"(g));
+  asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc) : "h"(v0), "h"(g0));
+  asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc) : "h"(v1), "h"(g1));
+}
+template <> __device__ __forceinline__ float dot16<__nv_bfloat16>(const uint4& v, const uint4& g, float acc) {
+  float a0 = acc, a1 = 0.f;    // two chains for ILP
+  dot_mixed_bf16(a0, v.x, g.x); dot_mixed_bf16(a1, v.y, g.y); dot_mixed_bf16(a0, v.z, g.z); dot_mixed_bf16(a1, v.w, g.w);
+  return a0 + a1;
+}
+template <> __device__ __forceinline__ float dot16<__half>(const uint4& v, const uint4& g, float acc) {
+  float a0 = acc, a1 = 0.f;
+  dot_mixed_f16(a0, v.x, g.x); dot_mixed_f16(a1, v.y, g.y); dot_mixed_f16(a0, v.z, g.z); dot_mixed_f16(a1, v.w, g.w);
+  return a0 + a1;
+}
+
 }  // namespace msda

@@ -27,6 +27,66 @@
 namespace msda {
 
 // =====================================================================================================
+// Shared-memory staging of a warp's sampling locations / attention weights (and, in backward, of the
+// gradients that replace them in place).  The warp's pairs are contiguous in global memory, so the copies
+// are plain coalesced 128-bit transfers; each pair's row gets 16 bytes of padding so that the G-lane groups
+// of a warp read their rows from distinct banks.
+// =====================================================================================================
+struct WarpStage {
+  float* loc;        // [GPW][2*LP + 4]
+  float* attn;       // [GPW][LP + 4]
+  int loc_stride, attn_stride;
+};
+
+__device__ __forceinline__ void stage_in(const WarpStage& ws, const float* __restrict__ gl, const float* __restrict__ ga,
+                                         int nvalid, int LP, int lane) {
+  if ((LP & 3) == 0) {
+    const int lv = LP / 2, av = LP / 4;     // float4s per pair row
+    for (int i = lane; i < nvalid * lv; i += 32) {
+      const int r = i / lv, k = i - r * lv;
+      *reinterpret_cast<float4*>(ws.loc + r * ws.loc_stride + 4 * k) = __ldg(reinterpret_cast<const float4*>(gl) + i);
+    }
+    for (int i = lane; i < nvalid * av; i += 32) {
+      const int r = i / av, k = i - r * av;
+      *reinterpret_cast<float4*>(ws.attn + r * ws.attn_stride + 4 * k) = __ldg(reinterpret_cast<const float4*>(ga) + i);
+    }
+  } else {
+    for (int i = lane; i < nvalid * 2 * LP; i += 32) {
+      const int r = i / (2 * LP), k = i - r * 2 * LP;
+      ws.loc[r * ws.loc_stride + k] = __ldg(gl + i);
+    }
+    for (int i = lane; i < nvalid * LP; i += 32) {
+      const int r = i / LP, k = i - r * LP;
+      ws.attn[r * ws.attn_stride + k] = __ldg(ga + i);
+    }
+  }
+}
+
+__device__ __forceinline__ void stage_out(const WarpStage& ws, float* __restrict__ gl, float* __restrict__ ga,
+                                          int nvalid, int LP, int lane) {
+  if ((LP & 3) == 0) {
+    const int lv = LP / 2, av = LP / 4;
+    for (int i = lane; i < nvalid * lv; i += 32) {
+      const int r = i / lv, k = i - r * lv;
+      __stcs(reinterpret_cast<float4*>(gl) + i, *reinterpret_cast<const float4*>(ws.loc + r * ws.loc_stride + 4 * k));
+    }
+    for (int i = lane; i < nvalid * av; i += 32) {
+      const int r = i / av, k = i - r * av;
+      __stcs(reinterpret_cast<float4*>(ga) + i, *reinterpret_cast<const float4*>(ws.attn + r * ws.attn_stride + 4 * k));
+    }
+  } else {
+    for (int i = lane; i < nvalid * 2 * LP; i += 32) {
+      const int r = i / (2 * LP), k = i - r * 2 * LP;
+      gl[i] = ws.loc[r * ws.loc_stride + k];
+    }
+    for (int i = lane; i < nvalid * LP; i += 32) {
+      const int r = i / LP, k = i - r * LP;
+      ga[i] = ws.attn[r * ws.attn_stride + k];
+    }
+  }
+}
+
+// =====================================================================================================
 // Forward, vector path
 // =====================================================================================================
 template <typename T, int D>
@@ -45,52 +105,28 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   load_level_meta(meta, shapes, lsi, L);
 
   const int LP = L * P;
-  const int loc_stride = 2 * LP + 4;   // floats; +16 B pad keeps the per-group rows on distinct banks
-  const int attn_stride = LP + 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / G, c = lane % G;
-  float* wloc = smem + warp * GPW * (loc_stride + attn_stride);
-  float* wattn = wloc + GPW * loc_stride;
+  WarpStage ws;
+  ws.loc_stride = 2 * LP + 4;
+  ws.attn_stride = LP + 4;
+  ws.loc = smem + warp * GPW * (ws.loc_stride + ws.attn_stride);
+  ws.attn = ws.loc + GPW * ws.loc_stride;
 
   const int pair0 = (blockIdx.x * kWarps + warp) * GPW;
   const int nvalid = min(GPW, total_pairs - pair0);
   if (nvalid <= 0) return;
-
-  // ---- stage this warp's sampling locations and attention weights (contiguous in global memory) ----
-  {
-    const float* gl = loc + static_cast<size_t>(pair0) * (2 * LP);
-    const float* ga = attn + static_cast<size_t>(pair0) * LP;
-    if ((LP & 3) == 0) {
-      const int lv = LP / 2, av = LP / 4;     // float4s per pair row
-      for (int i = lane; i < nvalid * lv; i += 32) {
-        const int r = i / lv, k = i - r * lv;
-        *reinterpret_cast<float4*>(wloc + r * loc_stride + 4 * k) = __ldg(reinterpret_cast<const float4*>(gl) + i);
-      }
-      for (int i = lane; i < nvalid * av; i += 32) {
-        const int r = i / av, k = i - r * av;
-        *reinterpret_cast<float4*>(wattn + r * attn_stride + 4 * k) = __ldg(reinterpret_cast<const float4*>(ga) + i);
-      }
-    } else {
-      for (int i = lane; i < nvalid * 2 * LP; i += 32) {
-        const int r = i / (2 * LP), k = i - r * 2 * LP;
-        wloc[r * loc_stride + k] = __ldg(gl + i);
-      }
-      for (int i = lane; i < nvalid * LP; i += 32) {
-        const int r = i / LP, k = i - r * LP;
-        wattn[r * attn_stride + k] = __ldg(ga + i);
-      }
-    }
-  }
+  stage_in(ws, loc + static_cast<size_t>(pair0) * (2 * LP), attn + static_cast<size_t>(pair0) * LP, nvalid, LP, lane);
   __syncwarp();
   if (g >= nvalid) return;
 
   const int pair = pair0 + g;
   const int m = pair % M;
   const int b = (pair / M) / Lq;
-  const size_t pix_stride = static_cast<size_t>(M) * D;            // elements between neighbouring pixels
-  const T* vb = value + static_cast<size_t>(b) * S * pix_stride + m * D + c * VEC;
-  const float* myloc = wloc + g * loc_stride;
-  const float* myattn = wattn + g * attn_stride;
+  const uint32_t pix_bytes = static_cast<uint32_t>(M) * D * sizeof(T);        // bytes between neighbouring pixels
+  const char* vb = reinterpret_cast<const char*>(value) + (static_cast<size_t>(b) * S * M + m) * (D * sizeof(T)) + c * 16;
+  const float* myloc = ws.loc + g * ws.loc_stride;
+  const float* myattn = ws.attn + g * ws.attn_stride;
 
   float acc[VEC];
 #pragma unroll
@@ -98,40 +134,51 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 
   for (int l = 0; l < L; ++l) {
     const int H = meta.H[l], W = meta.W[l];
-    const T* vl = vb + static_cast<size_t>(meta.start[l]) * pix_stride;
-#pragma unroll 4
+    const float Hf = static_cast<float>(H), Wf = static_cast<float>(W);
+    const char* vl = vb + static_cast<size_t>(meta.start[l]) * pix_bytes;
+#pragma unroll 2
     for (int p = 0; p < P; ++p) {
       const float2 xy = *reinterpret_cast<const float2*>(myloc + 2 * (l * P + p));
       const float a = myattn[l * P + p];
-      const Footprint<float> fp = make_footprint<float>(xy.x, xy.y, H, W);
-      const T* p00 = vl + (static_cast<ptrdiff_t>(fp.h0) * W + fp.w0) * static_cast<ptrdiff_t>(pix_stride);
-      const uint4 zero = make_uint4(0, 0, 0, 0);
-      const uint4 u00 = fp.v00 ? ldg16(p00) : zero;
-      const uint4 u01 = fp.v01 ? ldg16(p00 + pix_stride) : zero;
-      const uint4 u10 = fp.v10 ? ldg16(p00 + static_cast<size_t>(W) * pix_stride) : zero;
-      const uint4 u11 = fp.v11 ? ldg16(p00 + static_cast<size_t>(W + 1) * pix_stride) : zero;
-      const float w00 = fp.hh * fp.hw * a, w01 = fp.hh * fp.lw * a, w10 = fp.lh * fp.hw * a, w11 = fp.lh * fp.lw * a;
-      float f[VEC];
-      unpack16<T>(u00, f);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w00, f[i], acc[i]);
-      unpack16<T>(u01, f);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w01, f[i], acc[i]);
-      unpack16<T>(u10, f);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w10, f[i], acc[i]);
-      unpack16<T>(u11, f);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w11, f[i], acc[i]);
+      const Taps t = make_taps(xy.x, xy.y, H, W, Hf, Wf);
+      // pixel index * pixel stride fits 32 bits (validated on the host): one IMAD.WIDE per corner
+      const uint4 u00 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i00) * pix_bytes));
+      const uint4 u01 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i01) * pix_bytes));
+      const uint4 u10 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i10) * pix_bytes));
+      const uint4 u11 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i11) * pix_bytes));
+      const float ah = t.hhm * a, al = t.lhm * a;
+      axpy16<T>(acc, u00, make_weight<T>(ah * t.hwm));
+      axpy16<T>(acc, u01, make_weight<T>(ah * t.lwm));
+      axpy16<T>(acc, u10, make_weight<T>(al * t.hwm));
+      axpy16<T>(acc, u11, make_weight<T>(al * t.lwm));
     }
   }
-  *reinterpret_cast<uint4*>(out + static_cast<size_t>(pair) * D + c * VEC) = pack16<T>(acc);
+  __stcs(reinterpret_cast<uint4*>(out + static_cast<size_t>(pair) * D + c * VEC), pack16<T>(acc));
 }
 
 // =====================================================================================================
 // Backward, vector path
 // =====================================================================================================
+// Reduce-scatter of per-lane partial sums inside a G-lane group: every lane enters with R values for each of
+// G consecutive sampling points and leaves with the group totals of the point whose index equals its lane
+// position c.  (R*(G-1) shuffles per G points instead of R*log2(G) per point.)
+template <int G, int R>
+__device__ __forceinline__ void group_reduce_scatter(float (&v)[G][R], int c) {
+#pragma unroll
+  for (int s = G / 2; s >= 1; s >>= 1) {
+    const bool upper = (c & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float keep = upper ? v[j + s][r] : v[j][r];
+        const float send = upper ? v[j][r] : v[j + s][r];
+        v[j][r] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+      }
+    }
+  }
+}
+
 // GV16 = false: grad_value contributions go to an fp32 buffer `gv32` laid out like value
 //               (grad_value itself for T = float, the caller's scratch for 16-bit T) with red.v4.f32.
 // GV16 = true : 16-bit T only; contributions are rounded to T and added with packed 16-bit red.
@@ -146,163 +193,148 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   constexpr int VEC = 16 / sizeof(T);
   constexpr int G = D / VEC;
   constexpr int GPW = 32 / G;
+  constexpr bool k16 = sizeof(T) == 2;
 
   extern __shared__ __align__(16) float smem[];
   __shared__ LevelMeta meta;
   load_level_meta(meta, shapes, lsi, L);
 
   const int LP = L * P;
-  const int loc_stride = 2 * LP + 4;
-  const int attn_stride = LP + 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / G, c = lane % G;
-  float* wloc = smem + warp * GPW * (loc_stride + attn_stride);
-  float* wattn = wloc + GPW * loc_stride;
+  WarpStage ws;
+  ws.loc_stride = 2 * LP + 4;
+  ws.attn_stride = LP + 4;
+  ws.loc = smem + warp * GPW * (ws.loc_stride + ws.attn_stride);
+  ws.attn = ws.loc + GPW * ws.loc_stride;
 
   const int pair0 = (blockIdx.x * kWarps + warp) * GPW;
   const int nvalid = min(GPW, total_pairs - pair0);
   if (nvalid <= 0) return;
-
-  const float* gl = loc + static_cast<size_t>(pair0) * (2 * LP);
-  const float* ga = attn + static_cast<size_t>(pair0) * LP;
-  const bool vec_rows = (LP & 3) == 0;
-  if (vec_rows) {
-    const int lv = LP / 2, av = LP / 4;
-    for (int i = lane; i < nvalid * lv; i += 32) {
-      const int r = i / lv, k = i - r * lv;
-      *reinterpret_cast<float4*>(wloc + r * loc_stride + 4 * k) = __ldg(reinterpret_cast<const float4*>(gl) + i);
-    }
-    for (int i = lane; i < nvalid * av; i += 32) {
-      const int r = i / av, k = i - r * av;
-      *reinterpret_cast<float4*>(wattn + r * attn_stride + 4 * k) = __ldg(reinterpret_cast<const float4*>(ga) + i);
-    }
-  } else {
-    for (int i = lane; i < nvalid * 2 * LP; i += 32) {
-      const int r = i / (2 * LP), k = i - r * 2 * LP;
-      wloc[r * loc_stride + k] = __ldg(gl + i);
-    }
-    for (int i = lane; i < nvalid * LP; i += 32) {
-      const int r = i / LP, k = i - r * LP;
-      wattn[r * attn_stride + k] = __ldg(ga + i);
-    }
-  }
+  stage_in(ws, loc + static_cast<size_t>(pair0) * (2 * LP), attn + static_cast<size_t>(pair0) * LP, nvalid, LP, lane);
   __syncwarp();
 
   // Lanes of padding groups (tail warp only) stay in the loop so that the full-mask shuffles are legal;
-  // they read pair 0 of the warp and never write.
+  // they shadow pair 0 of the warp and never write.
   const bool active = g < nvalid;
   const int pair = pair0 + (active ? g : 0);
   const int m = pair % M;
   const int b = (pair / M) / Lq;
-  const size_t pix_stride = static_cast<size_t>(M) * D;
-  const size_t img_off = static_cast<size_t>(b) * S * pix_stride + m * D + c * VEC;
-  const T* vb = value + img_off;
-  float* myloc = wloc + (active ? g : 0) * loc_stride;
-  float* myattn = wattn + (active ? g : 0) * attn_stride;
+  const uint32_t pix_bytes = static_cast<uint32_t>(M) * D * sizeof(T);
+  const size_t img_pix = static_cast<size_t>(b) * S * M + m;                     // in units of head slices
+  const char* vb = reinterpret_cast<const char*>(value) + img_pix * (D * sizeof(T)) + c * 16;
+  float* myloc = ws.loc + (active ? g : 0) * ws.loc_stride;
+  float* myattn = ws.attn + (active ? g : 0) * ws.attn_stride;
 
-  float go[VEC];
-  unpack16<T>(ldg16(grad_out + static_cast<size_t>(pair) * D + c * VEC), go);
+  // grad_out of this pair: raw 16 bytes in the value layout (for the dot products) and, for the fp32
+  // scatter of 16-bit types, the fp32 values of the channels this lane adds: lanes of a group then cover
+  // 64 contiguous bytes per red.v4.f32 (whole 32-byte sectors) instead of four half-sectors.
+  const T* go_row = grad_out + static_cast<size_t>(pair) * D;
+  const uint4 go_raw = ldg16(go_row + c * VEC);
+  float go_s[VEC];                       // channels [4c, 4c+4) and, for 16-bit T, [D/2 + 4c, D/2 + 4c + 4)
+  if constexpr (k16 && !GV16) {
+    const uint2 lo = __ldg(reinterpret_cast<const uint2*>(go_row + 4 * c));
+    const uint2 hi = __ldg(reinterpret_cast<const uint2*>(go_row + D / 2 + 4 * c));
+    float t8[8];
+    unpack16<T>(make_uint4(lo.x, lo.y, hi.x, hi.y), t8);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) go_s[i] = t8[i];
+  } else {
+    unpack16<T>(go_raw, go_s);
+  }
+  // element offset of this lane's first scatter channel inside a head slice
+  const int sc0 = (k16 && !GV16) ? 4 * c : c * VEC;
+  float* gv32_base = gv32 + img_pix * D + sc0;
+  T* gv16_base = gv16 + img_pix * D + c * VEC;
+  const uint32_t pix_elems = static_cast<uint32_t>(M) * D;
 
-  for (int l = 0; l < L; ++l) {
-    const int H = meta.H[l], W = meta.W[l];
-    const size_t lvl_off = static_cast<size_t>(meta.start[l]) * pix_stride;
-    const T* vl = vb + lvl_off;
-#pragma unroll 2
-    for (int p = 0; p < P; ++p) {
-      const int lp = l * P + p;
-      const float2 xy = *reinterpret_cast<const float2*>(myloc + 2 * lp);
-      const float a = myattn[lp];
-      const Footprint<float> fp = make_footprint<float>(xy.x, xy.y, H, W);
-      const ptrdiff_t o00 = (static_cast<ptrdiff_t>(fp.h0) * W + fp.w0) * static_cast<ptrdiff_t>(pix_stride);
-      const ptrdiff_t o01 = o00 + static_cast<ptrdiff_t>(pix_stride);
-      const ptrdiff_t o10 = o00 + static_cast<ptrdiff_t>(W) * static_cast<ptrdiff_t>(pix_stride);
-      const ptrdiff_t o11 = o10 + static_cast<ptrdiff_t>(pix_stride);
-      const uint4 zero = make_uint4(0, 0, 0, 0);
-      const uint4 u00 = fp.v00 ? ldg16(vl + o00) : zero;
-      const uint4 u01 = fp.v01 ? ldg16(vl + o01) : zero;
-      const uint4 u10 = fp.v10 ? ldg16(vl + o10) : zero;
-      const uint4 u11 = fp.v11 ? ldg16(vl + o11) : zero;
+  // Points are processed in chunks of CH; groups of up to 8 lanes reduce-scatter a chunk of G points at once,
+  // wider groups (D = 64 fp32, D = 128) fall back to one butterfly per point to keep registers in check.
+  constexpr int CH = (G <= 8) ? G : 1;
+  float part[CH][3];                     // per point of the current chunk: (grad_attn, grad_x, grad_y) partials
+  int l = 0, p = 0;
+  int H = meta.H[0], W = meta.W[0];
+  float Hf = static_cast<float>(H), Wf = static_cast<float>(W);
+  size_t lvl_pix = static_cast<size_t>(meta.start[0]);
 
-      // ---- grad_value: corner_weight * attn * grad_out, scattered with packed reductions ----
-      if (active) {
-        const float w[4] = {fp.hh * fp.hw * a, fp.hh * fp.lw * a, fp.lh * fp.hw * a, fp.lh * fp.lw * a};
-        const bool ok[4] = {fp.v00, fp.v01, fp.v10, fp.v11};
-        const ptrdiff_t off[4] = {o00, o01, o10, o11};
+  for (int lp0 = 0; lp0 < LP; lp0 += CH) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (ok[k]) {
-            float r[VEC];
+    for (int j = 0; j < CH; ++j) {
+      const int lp = lp0 + j;
+      if (lp < LP) {                      // warp-uniform
+        const float2 xy = *reinterpret_cast<const float2*>(myloc + 2 * lp);
+        const float a = myattn[lp];
+        const Taps t = make_taps(xy.x, xy.y, H, W, Hf, Wf);
+        const char* vl = vb + lvl_pix * pix_bytes;
+        const uint4 u00 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i00) * pix_bytes));
+        const uint4 u01 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i01) * pix_bytes));
+        const uint4 u10 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i10) * pix_bytes));
+        const uint4 u11 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i11) * pix_bytes));
+
+        // ---- grad_value: (corner weight * attn) * grad_out, scattered with packed reductions ----
+        if (active) {
+          const float ah = t.hhm * a, al = t.lhm * a;
+          const float w[4] = {ah * t.hwm, ah * t.lwm, al * t.hwm, al * t.lwm};
+          const int idx[4] = {t.i00, t.i01, t.i10, t.i11};
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) r[i] = w[k] * go[i];
-            if constexpr (GV16) {
-              red_add_16bit_x8<T>(gv16 + img_off + lvl_off + off[k], pack16<T>(r));
-            } else {
-              float* dst = gv32 + img_off + lvl_off + off[k];
+          for (int k = 0; k < 4; ++k) {
+            if (w[k] != 0.f) {            // invalid corners (and exact-zero weights) add nothing
+              const size_t e = (lvl_pix + idx[k]) * pix_elems;
+              float r[VEC];
 #pragma unroll
-              for (int i = 0; i < VEC; i += 4) red_add_f32x4(dst + i, r[i], r[i + 1], r[i + 2], r[i + 3]);
+              for (int i = 0; i < VEC; ++i) r[i] = w[k] * go_s[i];
+              if constexpr (GV16) {
+                red_add_16bit_x8<T>(gv16_base + e, pack16<T>(r));
+              } else if constexpr (k16) {
+                red_add_f32x4(gv32_base + e, r[0], r[1], r[2], r[3]);
+                red_add_f32x4(gv32_base + e + D / 2, r[4], r[5], r[6], r[7]);
+              } else {
+                red_add_f32x4(gv32_base + e, r[0], r[1], r[2], r[3]);
+              }
             }
           }
         }
-      }
 
-      // ---- per-corner dot products <v_c, grad_out>, reduced over the lane group ----
-      float f[VEC];
-      float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;
-      unpack16<T>(u00, f);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) d00 = fmaf(f[i], go[i], d00);
-      unpack16<T>(u01, f);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) d01 = fmaf(f[i], go[i], d01);
-      unpack16<T>(u10, f);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) d10 = fmaf(f[i], go[i], d10);
-      unpack16<T>(u11, f);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) d11 = fmaf(f[i], go[i], d11);
+        // ---- per-corner <value, grad_out>, then this lane's share of the three gradients ----
+        const float d00 = dot16<T>(u00, go_raw, 0.f), d01 = dot16<T>(u01, go_raw, 0.f);
+        const float d10 = dot16<T>(u10, go_raw, 0.f), d11 = dot16<T>(u11, go_raw, 0.f);
+        part[j][0] = t.hhm * (t.hwm * d00 + t.lwm * d01) + t.lhm * (t.hwm * d10 + t.lwm * d11);
+        part[j][1] = Wf * a * (t.hhm * (t.Rm * d01 - t.Lm * d00) + t.lhm * (t.Rm * d11 - t.Lm * d10));
+        part[j][2] = Hf * a * (t.hwm * (t.Bm * d10 - t.Tm * d00) + t.lwm * (t.Bm * d11 - t.Tm * d01));
+        if (++p == P) {                   // next level
+          p = 0; ++l;
+          if (l < L) {
+            H = meta.H[l]; W = meta.W[l]; Hf = static_cast<float>(H); Wf = static_cast<float>(W);
+            lvl_pix = static_cast<size_t>(meta.start[l]);
+          }
+        }
+      } else {
+        part[j][0] = 0.f; part[j][1] = 0.f; part[j][2] = 0.f;
+      }
+    }
+    int owner;                            // which point of the chunk this lane writes (-1: none)
+    if constexpr (CH == G) {
+      group_reduce_scatter<G, 3>(part, c);
+      owner = c;
+    } else {
 #pragma unroll
       for (int s = G / 2; s >= 1; s >>= 1) {
-        d00 += __shfl_xor_sync(0xffffffffu, d00, s);
-        d01 += __shfl_xor_sync(0xffffffffu, d01, s);
-        d10 += __shfl_xor_sync(0xffffffffu, d10, s);
-        d11 += __shfl_xor_sync(0xffffffffu, d11, s);
+        part[0][0] += __shfl_xor_sync(0xffffffffu, part[0][0], s);
+        part[0][1] += __shfl_xor_sync(0xffffffffu, part[0][1], s);
+        part[0][2] += __shfl_xor_sync(0xffffffffu, part[0][2], s);
       }
-      // grad_attn = bilinear(value) . grad_out ; grad_loc = attn * (W, H) * d(bilinear)/d(w, h) . grad_out
-      const float g_attn = fp.hh * fp.hw * d00 + fp.hh * fp.lw * d01 + fp.lh * fp.hw * d10 + fp.lh * fp.lw * d11;
-      const float g_x = static_cast<float>(W) * a * (fp.hh * (d01 - d00) + fp.lh * (d11 - d10));
-      const float g_y = static_cast<float>(H) * a * (fp.hw * (d10 - d00) + fp.lw * (d11 - d01));
-      __syncwarp();
-      if (active && c == 0) {   // in place: every lane of the group has already read (x, y, a) of this point
-        *reinterpret_cast<float2*>(myloc + 2 * lp) = make_float2(g_x, g_y);
-        myattn[lp] = g_attn;
-      }
+      owner = (c == 0) ? 0 : -1;
+    }
+    __syncwarp();
+    // the owner lane now holds the group totals of point lp0 + owner; every lane of the group has already
+    // read that point's (x, y, attn), so the gradients can replace them in place
+    if (active && owner >= 0 && lp0 + owner < LP) {
+      *reinterpret_cast<float2*>(myloc + 2 * (lp0 + owner)) = make_float2(part[0][1], part[0][2]);
+      myattn[lp0 + owner] = part[0][0];
     }
   }
   __syncwarp();
-
-  // ---- coalesced write-back of the staged gradients ----
-  float* ol = grad_loc + static_cast<size_t>(pair0) * (2 * LP);
-  float* oa = grad_attn + static_cast<size_t>(pair0) * LP;
-  if (vec_rows) {
-    const int lv = LP / 2, av = LP / 4;
-    for (int i = lane; i < nvalid * lv; i += 32) {
-      const int r = i / lv, k = i - r * lv;
-      reinterpret_cast<float4*>(ol)[i] = *reinterpret_cast<const float4*>(wloc + r * loc_stride + 4 * k);
-    }
-    for (int i = lane; i < nvalid * av; i += 32) {
-      const int r = i / av, k = i - r * av;
-      reinterpret_cast<float4*>(oa)[i] = *reinterpret_cast<const float4*>(wattn + r * attn_stride + 4 * k);
-    }
-  } else {
-    for (int i = lane; i < nvalid * 2 * LP; i += 32) {
-      const int r = i / (2 * LP), k = i - r * 2 * LP;
-      ol[i] = wloc[r * loc_stride + k];
-    }
-    for (int i = lane; i < nvalid * LP; i += 32) {
-      const int r = i / LP, k = i - r * LP;
-      oa[i] = wattn[r * attn_stride + k];
-    }
-  }
+  stage_out(ws, grad_loc + static_cast<size_t>(pair0) * (2 * LP), grad_attn + static_cast<size_t>(pair0) * LP, nvalid, LP, lane);
 }
 
 // fp32 accumulation buffer -> 16-bit grad_value (one rounding per element)
@@ -479,7 +511,11 @@ static int validate(const Problem& pr, int dtype, int im2col_step) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <typename T> static bool vec_supported(int D) { return D == 16 || D == 32 || D == 64 || D == 128; }
+// vector kernels: head dims with power-of-two lane groups, and per-image byte offsets that fit 32 bits
+template <typename T> static bool vec_supported(const Problem& pr) {
+  const bool d_ok = pr.D == 16 || pr.D == 32 || pr.D == 64 || pr.D == 128;
+  return d_ok && static_cast<unsigned long long>(pr.S) * pr.M * pr.D * sizeof(float) < (1ull << 32);
+}
 
 template <typename T, int D>
 static size_t vec_smem_bytes(int L, int P) {
@@ -516,7 +552,7 @@ template <typename T>
 static int launch_fwd(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
                       const void* loc, const void* attn, void* out, cudaStream_t st) {
   if constexpr (!std::is_same<T, double>::value) {
-    if (vec_supported<T>(pr.D)) {
+    if (vec_supported<T>(pr)) {
       switch (pr.D) {
         case 16: return launch_fwd_vec<T, 16>(pr, value, shapes, lsi, loc, attn, out, st);
         case 32: return launch_fwd_vec<T, 32>(pr, value, shapes, lsi, loc, attn, out, st);
@@ -574,7 +610,7 @@ static int launch_bwd(const Problem& pr, const void* value, const int64_t* shape
                       void* scratch, int flags, cudaStream_t st) {
   const size_t n_value = static_cast<size_t>(pr.N) * pr.S * pr.M * pr.D;
   constexpr bool k16 = sizeof(T) == 2;
-  const bool use16 = k16 && (flags & MSDA_BWD_GRAD_VALUE_16BIT_ATOMICS) && vec_supported<T>(pr.D);
+  const bool use16 = k16 && (flags & MSDA_BWD_GRAD_VALUE_16BIT_ATOMICS) && vec_supported<T>(pr);
   cudaError_t e = cudaMemsetAsync(gv, 0, n_value * sizeof(T), st);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (k16 && !use16) {
@@ -584,7 +620,7 @@ static int launch_bwd(const Problem& pr, const void* value, const int64_t* shape
   int rc;
   bool done = false;
   if constexpr (!std::is_same<T, double>::value) {
-    if (vec_supported<T>(pr.D)) {
+    if (vec_supported<T>(pr)) {
       float* gv32 = k16 ? static_cast<float*>(scratch) : static_cast<float*>(gv);
       switch (pr.D) {
         case 16: rc = launch_bwd_vec<T, 16>(pr, value, shapes, lsi, loc, attn, go, gv32, gv, gloc, gattn, use16, st); break;
@@ -701,7 +737,8 @@ extern "C" int msda_forward(const void* value, const int64_t* spatial_shapes, co
 
 extern "C" size_t msda_backward_scratch_bytes(int N, int S, int M, int D, int value_dtype, int flags) {
   if (value_dtype != MSDA_BF16 && value_dtype != MSDA_F16) return 0;
-  const bool vec = (D == 16 || D == 32 || D == 64 || D == 128);
+  const bool vec = (D == 16 || D == 32 || D == 64 || D == 128) &&
+                   static_cast<unsigned long long>(S) * M * D * sizeof(float) < (1ull << 32);
   if ((flags & MSDA_BWD_GRAD_VALUE_16BIT_ATOMICS) && vec) return 0;
   return static_cast<size_t>(N) * S * M * D * sizeof(float);
 }
