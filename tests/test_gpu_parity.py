@@ -280,3 +280,29 @@ def test_bf16_aux_inputs_are_accepted_and_grads_keep_their_dtype(ops):
     out = ops.MSDeformAttnFunction.apply(v, ss.to(dev), lsi.to(dev), lo, at, 64)
     out.sum().backward()
     assert lo.grad.dtype == torch.bfloat16 and at.grad.dtype == torch.bfloat16 and v.grad.dtype == torch.bfloat16
+
+
+def test_host_pipeline_matches_device_resident_path(ops):
+    """HostPipeline (pinned host operands, 3 streams, double-buffered) == direct extension-level calls."""
+    from vision_instance_seg_b200.host_pipeline import HostPipeline
+    from vision_instance_seg_b200 import MultiScaleDeformableAttention as MSDA
+    dev = torch.device("cuda:0")
+    problems = [random_problem(2, 8, 32, 150, [(16, 16), (8, 8)], 4, seed=40 + i, dtype=torch.float32) for i in range(5)]
+    ss, lsi = problems[0][1], problems[0][2]
+    pipe = HostPipeline(ss, lsi, dev)
+    outs = []
+    for value, _, _, loc, attn, go in problems:
+        h_in = [t.to(dt).pin_memory() for t, dt in ((value, torch.bfloat16), (loc, torch.float32), (attn, torch.float32), (go, torch.bfloat16))]
+        h_out = [torch.empty(2, 150, 256, dtype=torch.bfloat16).pin_memory(), torch.empty(value.shape, dtype=torch.bfloat16).pin_memory(),
+                 torch.empty(loc.shape, dtype=torch.float32).pin_memory(), torch.empty(attn.shape, dtype=torch.float32).pin_memory()]
+        pipe.submit(h_in, h_out)
+        outs.append((h_in, h_out))
+    pipe.synchronize()
+    assert pipe.h2d_bytes == sum(t.numel() * t.element_size() for h_in, _ in outs for t in h_in)
+    for h_in, h_out in outs:
+        d = [t.to(dev) for t in h_in]
+        out = MSDA.ms_deform_attn_forward(d[0], ss.to(dev), lsi.to(dev), d[1], d[2], 128)
+        gv, gl, ga = MSDA.ms_deform_attn_backward(d[0], ss.to(dev), lsi.to(dev), d[1], d[2], d[3], 128)
+        assert torch.equal(out.cpu(), h_out[0])
+        assert rel_to_max(h_out[1], gv) < 1e-2          # fp32 atomics: order-dependent in the last bits, then bf16 rounding
+        assert torch.equal(gl.cpu(), h_out[2]) and torch.equal(ga.cpu(), h_out[3])
