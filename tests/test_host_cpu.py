@@ -26,7 +26,7 @@ def test_header_declares_and_library_exports_every_symbol(built_library):
     lib = ctypes.CDLL(built_library)
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/msda_b200.h but not exported"
-    assert pkg.load_library().msda_abi_version() == 1
+    assert pkg.load_library().msda_abi_version() == 2
 
 
 def test_error_strings(built_library):
@@ -54,9 +54,16 @@ def test_argument_validation_without_gpu(built_library):
     assert lib.msda_forward(p + 4, p, p, p, p, p, *ok_dims, 0, 64, None) == -4
     assert lib.msda_forward(p, p, p, p, p, p, 6, 4, 1, 4, 1, 1, 1, 0, 4, None) == -5     # 6 % 4 != 0
     assert lib.msda_backward(p, p, p, p, p, p, p, p, p, None, 0, *ok_dims, 2, 64, 0, None) == -6  # bf16 needs scratch
-    assert lib.msda_backward_scratch_bytes(2, 10, 8, 32, _lib.MSDA_BF16, 0) == 2 * 10 * 8 * 32 * 4
-    assert lib.msda_backward_scratch_bytes(2, 10, 8, 32, _lib.MSDA_BF16, 1) == 0
-    assert lib.msda_backward_scratch_bytes(2, 10, 8, 32, _lib.MSDA_F32, 0) == 0
+    # (N, S, M, D, Lq, L, P, dtype, flags): fp32 accumulation = one float per value element ...
+    assert lib.msda_backward_scratch_bytes(2, 10, 8, 32, 7, 2, 4, _lib.MSDA_BF16, _lib.MSDA_BWD_GRAD_VALUE_FP32_ACCUM) == 2 * 10 * 8 * 32 * 4
+    # ... bucketed fp16 accumulation (default) = 256-byte control block + N * rows_bound * M * D halves,
+    # rows_bound = L * (ceil(Lq*P/depth) + 1) + 2*S
+    rows = 2 * ((7 * 4 + 31) // 32 + 1) + 2 * 10
+    assert lib.msda_backward_scratch_bytes(2, 10, 8, 32, 7, 2, 4, _lib.MSDA_BF16, 0) == 256 + 2 * rows * 8 * 32 * 2
+    rows4 = 2 * ((7 * 4 + 3) // 4 + 1) + 2 * 10
+    assert lib.msda_backward_scratch_bytes(2, 10, 8, 32, 7, 2, 4, _lib.MSDA_F16, _lib.accum_depth_flag(4)) == 256 + 2 * rows4 * 8 * 32 * 2
+    assert lib.msda_backward_scratch_bytes(2, 10, 8, 30, 7, 2, 4, _lib.MSDA_BF16, 0) == 2 * 10 * 8 * 30 * 4   # compat kernels
+    assert lib.msda_backward_scratch_bytes(2, 10, 8, 32, 7, 2, 4, _lib.MSDA_F32, 0) == 0
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -55,16 +55,21 @@ if __name__ == "__main__":
     parity("small_uni64", W.make_uniform_inputs, torch.float64, shapes=small, batch=2)
     parity("cfg1_enc", W.make_encoder_inputs, torch.float32, shapes=c1, batch=2)
     parity("cfg1_enc", W.make_encoder_inputs, torch.bfloat16, shapes=c1, batch=2)
-    parity("cfg1_enc", W.make_encoder_inputs, torch.bfloat16, flags=1, shapes=c1, batch=2)
+    parity("cfg1_enc", W.make_encoder_inputs, torch.bfloat16, flags=2, shapes=c1, batch=2)
+    parity("cfg1_enc", W.make_encoder_inputs, torch.bfloat16, flags=65535 << 8, shapes=c1, batch=2)
     parity("cfg1_enc", W.make_encoder_inputs, torch.float16, shapes=c1, batch=2)
     parity("cfg1_uni_d30", W.make_uniform_inputs, torch.float32, shapes=small, batch=2, head_dim=30)
     parity("cfg1_uni_d64", W.make_uniform_inputs, torch.float32, shapes=small, batch=2, head_dim=64)
     parity("cfg1_dec", W.make_decoder_inputs, torch.bfloat16, shapes=c1, batch=2)
     parity("cfg3_n2_enc", W.make_encoder_inputs, torch.bfloat16, shapes=c3, batch=2)
-    parity("cfg3_n2_enc", W.make_encoder_inputs, torch.bfloat16, flags=1, shapes=c3, batch=2)
+    parity("cfg3_n2_enc", W.make_encoder_inputs, torch.bfloat16, flags=2, shapes=c3, batch=2)
+    parity("cfg3_n2_enc", W.make_encoder_inputs, torch.bfloat16, flags=65535 << 8, shapes=c3, batch=2)
+    parity("cfg3_n2_enc", W.make_encoder_inputs, torch.bfloat16, flags=8 << 8, shapes=c3, batch=2)
     timing("cfg1", W.make_encoder_inputs, torch.float32, shapes=c1, batch=2)
     timing("cfg3", W.make_encoder_inputs, torch.bfloat16, shapes=c3, batch=16)
-    timing("cfg3", W.make_encoder_inputs, torch.bfloat16, flags=1, shapes=c3, batch=16)
+    timing("cfg3", W.make_encoder_inputs, torch.bfloat16, flags=2, shapes=c3, batch=16)
+    timing("cfg3", W.make_encoder_inputs, torch.bfloat16, flags=65535 << 8, shapes=c3, batch=16)
+    timing("cfg3", W.make_encoder_inputs, torch.bfloat16, flags=8 << 8, shapes=c3, batch=16)
     timing("cfg3_fp32", W.make_encoder_inputs, torch.float32, shapes=c3, batch=16)
     timing("cfg3_uniform", W.make_uniform_inputs, torch.bfloat16, shapes=c3, batch=16)
     timing("cfg4_dec", W.make_decoder_inputs, torch.bfloat16, shapes=c3, batch=16)

@@ -23,9 +23,10 @@ from . import _lib
 _DTYPES = {torch.float32: _lib.MSDA_F32, torch.float64: _lib.MSDA_F64,
            torch.bfloat16: _lib.MSDA_BF16, torch.float16: _lib.MSDA_F16}
 
-#: backward flags (see include/msda_b200.h); overridable per process with MSDA_B200_GRAD_VALUE_16BIT=1
-backward_flags = _lib.MSDA_BWD_GRAD_VALUE_16BIT_ATOMICS if os.environ.get("MSDA_B200_GRAD_VALUE_16BIT") == "1" \
-    else _lib.MSDA_BWD_DEFAULT
+#: backward flags (see include/msda_b200.h); MSDA_B200_FP32_ACCUM=1 forces fp32 accumulation of grad_value for
+#: 16-bit values, MSDA_B200_ACCUM_DEPTH=<n> overrides the fp16 bucket depth
+backward_flags = (_lib.MSDA_BWD_GRAD_VALUE_FP32_ACCUM if os.environ.get("MSDA_B200_FP32_ACCUM") == "1"
+                  else _lib.MSDA_BWD_DEFAULT) | _lib.accum_depth_flag(int(os.environ.get("MSDA_B200_ACCUM_DEPTH", "0")))
 
 
 def _require(t: torch.Tensor, name: str) -> None:
@@ -101,7 +102,7 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
         grad_attn = torch.empty(attn_weight.shape, dtype=aux, device=value.device)
         if grad_loc.numel() == 0 or value.numel() == 0:
             return [grad_value.zero_(), grad_loc.zero_(), grad_attn.zero_()]
-        nbytes = lib.msda_backward_scratch_bytes(N, S, M, D, code, backward_flags)
+        nbytes = lib.msda_backward_scratch_bytes(N, S, M, D, Lq, L, P, code, backward_flags)
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=value.device) if nbytes else None
         stream = torch.cuda.current_stream().cuda_stream
         rc = lib.msda_backward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), loc.data_ptr(), attn.data_ptr(),

@@ -17,7 +17,12 @@ _lib = None
 
 MSDA_F32, MSDA_F64, MSDA_BF16, MSDA_F16 = 0, 1, 2, 3
 MSDA_BWD_DEFAULT = 0
-MSDA_BWD_GRAD_VALUE_16BIT_ATOMICS = 1
+MSDA_BWD_GRAD_VALUE_FP32_ACCUM = 2
+
+
+def accum_depth_flag(depth: int) -> int:
+    """flags bits that override the fp16 accumulation depth (see include/msda_b200.h)."""
+    return (int(depth) & 0xFFFF) << 8
 
 #: every symbol include/msda_b200.h declares (tests check that the built library exports all of them)
 EXPORTED_SYMBOLS = (
@@ -48,7 +53,7 @@ def _declare(lib):
     lib.msda_forward.restype = i
     lib.msda_forward.argtypes = [vp, i64p, i64p, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]
     lib.msda_backward_scratch_bytes.restype = sz
-    lib.msda_backward_scratch_bytes.argtypes = [i, i, i, i, i, i]
+    lib.msda_backward_scratch_bytes.argtypes = [i, i, i, i, i, i, i, i, i]
     lib.msda_backward.restype = i
     lib.msda_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, vp, vp, vp, vp, sz,
                                   i, i, i, i, i, i, i, i, i, i, vp]

@@ -179,25 +179,43 @@ __device__ __forceinline__ void group_reduce_scatter(float (&v)[G][R], int c) {
   }
 }
 
+// Scale of the fp16 accumulation buffer (GV16 mode).  |grad_value[b, s, m, d]| <= sum_q |grad_out[b, q, m, d]| *
+// sum_p attn*bilinear <= Lq * max|grad_out| for ANY input (attention weights of a query sum to <= 1 in the
+// module; bilinear weights to <= 1), so with scale = the largest power of two such that
+// Lq * max|grad_out| * scale <= 2^15 no partial sum can overflow fp16 (max 65504), whatever the sampling
+// pattern.  ctrl[0] holds the bits of max|grad_out| (written by msda_absmax_kernel).
+__device__ __forceinline__ float f16_accum_scale(const uint32_t* __restrict__ ctrl, int Lq) {
+  const float bound = __uint_as_float(__ldg(ctrl)) * static_cast<float>(Lq);
+  if (!(bound > 0.f)) return 1.f;
+  int e;
+  frexpf(bound, &e);                         // bound = f * 2^e, f in [0.5, 1)  =>  bound <= 2^e
+  return ldexpf(1.f, max(-100, min(100, 15 - e)));
+}
+
 // GV16 = false: grad_value contributions go to an fp32 buffer `gv32` laid out like value
 //               (grad_value itself for T = float, the caller's scratch for 16-bit T) with red.v4.f32.
-// GV16 = true : 16-bit T only; contributions are rounded to T and added with packed 16-bit red.
+// GV16 = true : 16-bit T only; contributions are scaled (f16_accum_scale), rounded to fp16 and added with
+//               packed red.global.add.noftz.v4.f16x2 into an fp16 buffer `gv16` laid out like value: half the
+//               reduction bytes of the fp32 path (the SM->L2 reduction path is what bounds this kernel).
 template <typename T, int D, bool GV16>
 __global__ void __launch_bounds__(kThreads)
 msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                     const float* __restrict__ attn, const T* __restrict__ grad_out,
-                    float* __restrict__ gv32, T* __restrict__ gv16,
+                    float* __restrict__ gv32, __half* __restrict__ gv16, const uint32_t* __restrict__ ctrl,
                     float* __restrict__ grad_loc, float* __restrict__ grad_attn,
-                    int S, int M, int Lq, int L, int P, int total_pairs) {
+                    int S, int M, int Lq, int L, int P, int total_pairs, int depth) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr int G = D / VEC;
   constexpr int GPW = 32 / G;
   constexpr bool k16 = sizeof(T) == 2;
+  float gv_scale = 1.f;
+  if constexpr (GV16) gv_scale = f16_accum_scale(ctrl, Lq);
 
   extern __shared__ __align__(16) float smem[];
   __shared__ LevelMeta meta;
   load_level_meta(meta, shapes, lsi, L);
+  if constexpr (GV16) build_accum_layout(meta, L, Lq, P, depth);
 
   const int LP = L * P;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -245,7 +263,16 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   // element offset of this lane's first scatter channel inside a head slice
   const int sc0 = (k16 && !GV16) ? 4 * c : c * VEC;
   float* gv32_base = gv32 + img_pix * D + sc0;
-  T* gv16_base = gv16 + img_pix * D + c * VEC;
+  const int q = (pair / M) % Lq;
+  // bucketed fp16 accumulator: image b starts at row b*accStride; the head / channel offset is the same
+  __half* gv16_base = nullptr;
+  size_t acc_row = 0;                     // first accumulator row of (this query's bucket of) the current level
+  if constexpr (GV16) {
+    gv16_base = gv16 + (static_cast<size_t>(b) * meta.accStride * M + m) * D + c * VEC;
+    acc_row = static_cast<size_t>(meta.accBase[0]) + static_cast<size_t>(q % meta.accK[0]) * (meta.H[0] * meta.W[0]);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) go_s[i] *= gv_scale;      // exact: power-of-two scale
+  }
   const uint32_t pix_elems = static_cast<uint32_t>(M) * D;
 
   // Points are processed in chunks of CH; groups of up to 8 lanes reduce-scatter a chunk of G points at once,
@@ -284,7 +311,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 #pragma unroll
               for (int i = 0; i < VEC; ++i) r[i] = w[k] * go_s[i];
               if constexpr (GV16) {
-                red_add_16bit_x8<T>(gv16_base + e, pack16<T>(r));
+                red_add_16bit_x8<__half>(gv16_base + (acc_row + idx[k]) * pix_elems, pack16<__half>(r));
               } else if constexpr (k16) {
                 red_add_f32x4(gv32_base + e, r[0], r[1], r[2], r[3]);
                 red_add_f32x4(gv32_base + e + D / 2, r[4], r[5], r[6], r[7]);
@@ -306,6 +333,8 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
           if (l < L) {
             H = meta.H[l]; W = meta.W[l]; Hf = static_cast<float>(H); Wf = static_cast<float>(W);
             lvl_pix = static_cast<size_t>(meta.start[l]);
+            if constexpr (GV16)
+              acc_row = static_cast<size_t>(meta.accBase[l]) + static_cast<size_t>(q % meta.accK[l]) * (H * W);
           }
         }
       } else {
@@ -347,6 +376,60 @@ msda_round_scratch_kernel(const float* __restrict__ src, T* __restrict__ dst, si
     const float4 b = __ldcs(reinterpret_cast<const float4*>(src) + 2 * i + 1);
     const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     reinterpret_cast<uint4*>(dst)[i] = pack16<T>(f);
+  }
+}
+
+// max |x| over a 16-bit tensor -> ctrl[0] (bits of a non-negative float order like unsigned integers)
+template <typename T>
+__global__ void __launch_bounds__(256)
+msda_absmax_kernel(const T* __restrict__ x, size_t n8, uint32_t* __restrict__ ctrl) {
+  float m = 0.f;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float f[8];
+    unpack16<T>(__ldg(reinterpret_cast<const uint4*>(x) + i), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m = fmaxf(m, fabsf(f[k]));
+  }
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(ctrl, __float_as_uint(m));
+}
+
+// bucketed, scaled fp16 accumulation buffer -> 16-bit grad_value: sum the K_l copies in fp32, unscale, round once
+template <typename T>
+__global__ void __launch_bounds__(256)
+msda_round_f16_buckets_kernel(const __half* __restrict__ acc, T* __restrict__ dst, const int64_t* __restrict__ shapes,
+                              const int64_t* __restrict__ lsi, const uint32_t* __restrict__ ctrl,
+                              int N, int S, int M, int D, int Lq, int L, int P, int depth) {
+  __shared__ LevelMeta meta;
+  load_level_meta(meta, shapes, lsi, L);
+  build_accum_layout(meta, L, Lq, P, depth);
+  const float inv = 1.f / f16_accum_scale(ctrl, Lq);        // exact: power of two
+  const int vec_per_pix = M * D / 8;
+  const size_t total = static_cast<size_t>(N) * S * vec_per_pix;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t pix = i / vec_per_pix;
+    const int v = static_cast<int>(i - pix * vec_per_pix);
+    const int b = static_cast<int>(pix / S);
+    const int s = static_cast<int>(pix - static_cast<size_t>(b) * S);
+    int l = 0;
+    while (l + 1 < L && s >= meta.start[l + 1]) ++l;
+    const int hw = meta.H[l] * meta.W[l];
+    const size_t row0 = static_cast<size_t>(b) * meta.accStride + meta.accBase[l] + (s - meta.start[l]);
+    float sum[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum[k] = 0.f;
+    for (int k = 0; k < meta.accK[l]; ++k) {
+      float f[8];
+      unpack16<__half>(__ldcs(reinterpret_cast<const uint4*>(acc) + (row0 + static_cast<size_t>(k) * hw) * vec_per_pix + v), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum[j] *= inv;
+    reinterpret_cast<uint4*>(dst)[i] = pack16<T>(sum);
   }
 }
 
@@ -466,6 +549,18 @@ msda_round_scratch_any_kernel(const float* __restrict__ src, T* __restrict__ dst
 // =====================================================================================================
 // Host side
 // =====================================================================================================
+constexpr size_t kF16CtrlBytes = 256;      // control block in front of the fp16 accumulation buffer
+constexpr int kDefaultAccumDepth = 32;     // expected adds per fp16 accumulator element (see build_accum_layout)
+
+static int accum_depth(int flags) {
+  const int d = (flags >> 8) & 0xffff;
+  return d > 0 ? d : kDefaultAccumDepth;
+}
+
+static size_t f16_scratch_bytes(int N, int S, int M, int D, int Lq, int L, int P, int depth) {
+  const long long rows = accum_rows_bound(S, L, Lq, P, depth);
+  return kF16CtrlBytes + static_cast<size_t>(N) * static_cast<size_t>(rows) * M * D * sizeof(__half);
+}
 static thread_local int g_last_launches = 0;
 static std::atomic<long long> g_total_launches{0};
 
@@ -572,8 +667,8 @@ static int launch_fwd(const Problem& pr, const void* value, const int64_t* shape
 
 template <typename T, int D>
 static int launch_bwd_vec(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
-                          const void* loc, const void* attn, const void* go, float* gv32, void* gv16,
-                          void* gloc, void* gattn, bool use16, cudaStream_t st) {
+                          const void* loc, const void* attn, const void* go, float* gv32, __half* gv16,
+                          const uint32_t* ctrl, void* gloc, void* gattn, bool use16, int depth, cudaStream_t st) {
   constexpr int GPW = 32 / (D / (16 / static_cast<int>(sizeof(T))));
   const size_t smem = vec_smem_bytes<T, D>(pr.L, pr.P);
   if (smem > 200 * 1024) return MSDA_ERR_BAD_SHAPE;
@@ -587,8 +682,8 @@ static int launch_bwd_vec(const Problem& pr, const void* value, const int64_t* s
       ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD, st);
       msda_bwd_vec_kernel<T, D, true><<<grid, kThreads, smem, st>>>(
           static_cast<const T*>(value), shapes, lsi, static_cast<const float*>(loc), static_cast<const float*>(attn),
-          static_cast<const T*>(go), nullptr, static_cast<T*>(gv16), static_cast<float*>(gloc),
-          static_cast<float*>(gattn), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs);
+          static_cast<const T*>(go), nullptr, gv16, ctrl, static_cast<float*>(gloc),
+          static_cast<float*>(gattn), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth);
       ++g_last_launches, ++g_total_launches;
       return static_cast<int>(cudaGetLastError());
     }
@@ -598,8 +693,8 @@ static int launch_bwd_vec(const Problem& pr, const void* value, const int64_t* s
   ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD, st);
   msda_bwd_vec_kernel<T, D, false><<<grid, kThreads, smem, st>>>(
       static_cast<const T*>(value), shapes, lsi, static_cast<const float*>(loc), static_cast<const float*>(attn),
-      static_cast<const T*>(go), gv32, nullptr, static_cast<float*>(gloc), static_cast<float*>(gattn),
-      pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs);
+      static_cast<const T*>(go), gv32, nullptr, nullptr, static_cast<float*>(gloc), static_cast<float*>(gattn),
+      pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth);
   ++g_last_launches, ++g_total_launches;
   return static_cast<int>(cudaGetLastError());
 }
@@ -610,12 +705,32 @@ static int launch_bwd(const Problem& pr, const void* value, const int64_t* shape
                       void* scratch, int flags, cudaStream_t st) {
   const size_t n_value = static_cast<size_t>(pr.N) * pr.S * pr.M * pr.D;
   constexpr bool k16 = sizeof(T) == 2;
-  const bool use16 = k16 && (flags & MSDA_BWD_GRAD_VALUE_16BIT_ATOMICS) && vec_supported<T>(pr);
-  cudaError_t e = cudaMemsetAsync(gv, 0, n_value * sizeof(T), st);
-  if (e != cudaSuccess) return static_cast<int>(e);
-  if (k16 && !use16) {
+  const bool use16 = k16 && !(flags & MSDA_BWD_GRAD_VALUE_FP32_ACCUM) && vec_supported<T>(pr);
+  const int depth = accum_depth(flags);
+  // 16-bit values accumulate in the scratch and grad_value is fully overwritten by the rounding pass, so only
+  // the buffer that receives the reductions is zeroed
+  cudaError_t e;
+  uint32_t* ctrl = nullptr;
+  __half* acc16 = nullptr;
+  if (!k16) {
+    e = cudaMemsetAsync(gv, 0, n_value * sizeof(T), st);
+  } else if (use16) {
+    e = cudaMemsetAsync(scratch, 0, f16_scratch_bytes(pr.N, pr.S, pr.M, pr.D, pr.Lq, pr.L, pr.P, depth), st);
+    ctrl = static_cast<uint32_t*>(scratch);
+    acc16 = reinterpret_cast<__half*>(static_cast<char*>(scratch) + kF16CtrlBytes);
+  } else {
     e = cudaMemsetAsync(scratch, 0, n_value * sizeof(float), st);
-    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if constexpr (k16) {
+    if (use16) {
+      const size_t n8 = static_cast<size_t>(pr.N) * pr.Lq * pr.M * pr.D / 8;     // D is a multiple of 16 here
+      const int grid = static_cast<int>(std::min<size_t>((n8 + 255) / 256, 148 * 8));
+      msda_absmax_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(go), n8, ctrl);
+      ++g_last_launches, ++g_total_launches;
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return static_cast<int>(e);
+    }
   }
   int rc;
   bool done = false;
@@ -623,10 +738,10 @@ static int launch_bwd(const Problem& pr, const void* value, const int64_t* shape
     if (vec_supported<T>(pr)) {
       float* gv32 = k16 ? static_cast<float*>(scratch) : static_cast<float*>(gv);
       switch (pr.D) {
-        case 16: rc = launch_bwd_vec<T, 16>(pr, value, shapes, lsi, loc, attn, go, gv32, gv, gloc, gattn, use16, st); break;
-        case 32: rc = launch_bwd_vec<T, 32>(pr, value, shapes, lsi, loc, attn, go, gv32, gv, gloc, gattn, use16, st); break;
-        case 64: rc = launch_bwd_vec<T, 64>(pr, value, shapes, lsi, loc, attn, go, gv32, gv, gloc, gattn, use16, st); break;
-        default: rc = launch_bwd_vec<T, 128>(pr, value, shapes, lsi, loc, attn, go, gv32, gv, gloc, gattn, use16, st); break;
+        case 16: rc = launch_bwd_vec<T, 16>(pr, value, shapes, lsi, loc, attn, go, gv32, acc16, ctrl, gloc, gattn, use16, depth, st); break;
+        case 32: rc = launch_bwd_vec<T, 32>(pr, value, shapes, lsi, loc, attn, go, gv32, acc16, ctrl, gloc, gattn, use16, depth, st); break;
+        case 64: rc = launch_bwd_vec<T, 64>(pr, value, shapes, lsi, loc, attn, go, gv32, acc16, ctrl, gloc, gattn, use16, depth, st); break;
+        default: rc = launch_bwd_vec<T, 128>(pr, value, shapes, lsi, loc, attn, go, gv32, acc16, ctrl, gloc, gattn, use16, depth, st); break;
       }
       done = true;
     }
@@ -650,7 +765,14 @@ static int launch_bwd(const Problem& pr, const void* value, const int64_t* shape
   }
   if (rc != 0) return rc;
   if constexpr (k16) {
-    if (!use16) {
+    if (use16) {
+      const size_t n8 = n_value / 8;
+      const int grid = static_cast<int>(std::min<size_t>((n8 + 255) / 256, 148 * 16));
+      msda_round_f16_buckets_kernel<T><<<grid, 256, 0, st>>>(acc16, static_cast<T*>(gv), shapes, lsi, ctrl, pr.N, pr.S,
+                                                            pr.M, pr.D, pr.Lq, pr.L, pr.P, depth);
+      ++g_last_launches, ++g_total_launches;
+      rc = static_cast<int>(cudaGetLastError());
+    } else {
       if ((n_value & 7) == 0) {
         const size_t n8 = n_value / 8;
         const int grid = static_cast<int>(std::min<size_t>((n8 + 255) / 256, 148 * 16));
@@ -673,7 +795,7 @@ static int launch_bwd(const Problem& pr, const void* value, const int64_t* shape
 // =====================================================================================================
 using namespace msda;
 
-extern "C" int msda_abi_version(void) { return 1; }
+extern "C" int msda_abi_version(void) { return 2; }
 
 extern "C" const char* msda_error_string(int code) {
   switch (code) {
@@ -735,11 +857,12 @@ extern "C" int msda_forward(const void* value, const int64_t* spatial_shapes, co
   return MSDA_ERR_BAD_DTYPE;
 }
 
-extern "C" size_t msda_backward_scratch_bytes(int N, int S, int M, int D, int value_dtype, int flags) {
+extern "C" size_t msda_backward_scratch_bytes(int N, int S, int M, int D, int Lq, int L, int P, int value_dtype, int flags) {
   if (value_dtype != MSDA_BF16 && value_dtype != MSDA_F16) return 0;
+  if (N <= 0 || S <= 0 || M <= 0 || D <= 0 || Lq <= 0 || L <= 0 || P <= 0) return 0;
   const bool vec = (D == 16 || D == 32 || D == 64 || D == 128) &&
                    static_cast<unsigned long long>(S) * M * D * sizeof(float) < (1ull << 32);
-  if ((flags & MSDA_BWD_GRAD_VALUE_16BIT_ATOMICS) && vec) return 0;
+  if (!(flags & MSDA_BWD_GRAD_VALUE_FP32_ACCUM) && vec) return f16_scratch_bytes(N, S, M, D, Lq, L, P, accum_depth(flags));
   return static_cast<size_t>(N) * S * M * D * sizeof(float);
 }
 
@@ -760,7 +883,7 @@ extern "C" int msda_backward(const void* value, const int64_t* spatial_shapes, c
   if (!aligned16(value) || !aligned16(sampling_loc) || !aligned16(attn_weight) || !aligned16(grad_output) ||
       !aligned16(grad_value) || !aligned16(grad_sampling_loc) || !aligned16(grad_attn_weight) || !aligned16(scratch))
     return MSDA_ERR_MISALIGNED;
-  const size_t need = msda_backward_scratch_bytes(N, S, M, D, value_dtype, flags);
+  const size_t need = msda_backward_scratch_bytes(N, S, M, D, Lq, L, P, value_dtype, flags);
   if (need > 0 && (!scratch || scratch_bytes < need)) return MSDA_ERR_SCRATCH_TOO_SMALL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (value_dtype) {
