@@ -265,6 +265,42 @@ template <> __device__ __forceinline__ void axpy16<__half>(float* acc, const uin
   fma_mixed_f16(acc[6], u.w, false, w); fma_mixed_f16(acc[7], u.w, true, w);
 }
 
+// same, with the 16-bit weight taken from the low (hi = false) or high half of a packed weight pair
+template <typename T> __device__ __forceinline__ void axpy16_packed(float* acc, const uint4& u, uint32_t wpair, bool hi);
+__device__ __forceinline__ void fma_mixed_bf16_sel(float& acc, uint32_t v, bool vhi, uint32_t wpair, bool whi) {
+  unsigned short v0, v1, w0, w1;
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(v0), "=h"(v1) : "r"(v));
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(w0), "=h"(w1) : "r"(wpair));
+  asm("fma.rn.f32.bf16 %0, %1, %2, %0;" : "+f"(acc) : "h"(vhi ? v1 : v0), "h"(whi ? w1 : w0));
+}
+__device__ __forceinline__ void fma_mixed_f16_sel(float& acc, uint32_t v, bool vhi, uint32_t wpair, bool whi) {
+  unsigned short v0, v1, w0, w1;
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(v0), "=h"(v1) : "r"(v));
+  asm("mov.b32 {%0, %1}, %2;" : "=h"(w0), "=h"(w1) : "r"(wpair));
+  asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(acc) : "h"(vhi ? v1 : v0), "h"(whi ? w1 : w0));
+}
+template <> __device__ __forceinline__ void axpy16_packed<__nv_bfloat16>(float* acc, const uint4& u, uint32_t wp, bool hi) {
+  fma_mixed_bf16_sel(acc[0], u.x, false, wp, hi); fma_mixed_bf16_sel(acc[1], u.x, true, wp, hi);
+  fma_mixed_bf16_sel(acc[2], u.y, false, wp, hi); fma_mixed_bf16_sel(acc[3], u.y, true, wp, hi);
+  fma_mixed_bf16_sel(acc[4], u.z, false, wp, hi); fma_mixed_bf16_sel(acc[5], u.z, true, wp, hi);
+  fma_mixed_bf16_sel(acc[6], u.w, false, wp, hi); fma_mixed_bf16_sel(acc[7], u.w, true, wp, hi);
+}
+template <> __device__ __forceinline__ void axpy16_packed<__half>(float* acc, const uint4& u, uint32_t wp, bool hi) {
+  fma_mixed_f16_sel(acc[0], u.x, false, wp, hi); fma_mixed_f16_sel(acc[1], u.x, true, wp, hi);
+  fma_mixed_f16_sel(acc[2], u.y, false, wp, hi); fma_mixed_f16_sel(acc[3], u.y, true, wp, hi);
+  fma_mixed_f16_sel(acc[4], u.z, false, wp, hi); fma_mixed_f16_sel(acc[5], u.z, true, wp, hi);
+  fma_mixed_f16_sel(acc[6], u.w, false, wp, hi); fma_mixed_f16_sel(acc[7], u.w, true, wp, hi);
+}
+template <typename T> __device__ __forceinline__ uint32_t pack_weight_pair(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack_weight_pair<__nv_bfloat16>(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+template <> __device__ __forceinline__ uint32_t pack_weight_pair<__half>(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
 // ---- dot(v, g) over one 16-byte vector, fp32 accumulate (16-bit: exact products through FHFMA) ----------
 template <typename T> __device__ __forceinline__ float dot16(const uint4& v, const uint4& g, float acc);
 template <> __device__ __forceinline__ float dot16<float>(const uint4& v, const uint4& g, float acc) {

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <algorithm>
+#include <cstdlib>
 #include <atomic>
 #include <mutex>
 #include <type_traits>
@@ -25,6 +26,10 @@
 #include "../../include/msda_b200.h"
 
 namespace msda {
+
+#ifndef BWD_MIN_CTAS
+#define BWD_MIN_CTAS 3
+#endif
 
 // =====================================================================================================
 // Shared-memory staging of a warp's sampling locations / attention weights (and, in backward, of the
@@ -198,7 +203,7 @@ __device__ __forceinline__ float f16_accum_scale(const uint32_t* __restrict__ ct
 //               packed red.global.add.noftz.v4.f16x2 into an fp16 buffer `gv16` laid out like value: half the
 //               reduction bytes of the fp32 path (the SM->L2 reduction path is what bounds this kernel).
 template <typename T, int D, bool GV16>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, BWD_MIN_CTAS)
 msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                     const float* __restrict__ attn, const T* __restrict__ grad_out,
@@ -629,12 +634,12 @@ template <typename T, int D>
 static int launch_fwd_vec(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
                           const void* loc, const void* attn, void* out, cudaStream_t st) {
   constexpr int GPW = 32 / (D / (16 / static_cast<int>(sizeof(T))));
+  const int per_cta = kWarps * GPW;
+  const int grid = (pr.total_pairs + per_cta - 1) / per_cta;
   const size_t smem = vec_smem_bytes<T, D>(pr.L, pr.P);
   if (smem > 200 * 1024) return MSDA_ERR_BAD_SHAPE;
   cudaError_t e = allow_smem(msda_fwd_vec_kernel<T, D>, smem);
   if (e != cudaSuccess) return static_cast<int>(e);
-  const int per_cta = kWarps * GPW;
-  const int grid = (pr.total_pairs + per_cta - 1) / per_cta;
   ScopedKernelTimer timer(MSDA_KERNEL_FORWARD, st);
   msda_fwd_vec_kernel<T, D><<<grid, kThreads, smem, st>>>(
       static_cast<const T*>(value), shapes, lsi, static_cast<const float*>(loc), static_cast<const float*>(attn),
