@@ -48,7 +48,8 @@ enum {
   MSDA_ERR_BAD_DTYPE = -3,
   MSDA_ERR_MISALIGNED = -4,      /* a buffer is not 16-byte aligned */
   MSDA_ERR_IM2COL_STEP = -5,     /* N % min(N, im2col_step) != 0 (upstream assert kept) */
-  MSDA_ERR_SCRATCH_TOO_SMALL = -6
+  MSDA_ERR_SCRATCH_TOO_SMALL = -6,
+  MSDA_ERR_FUSED_UNSUPPORTED = -7 /* fused pre-op: head dim not in {16,32,64,128}, float64 values, or ref_dim not 2/4 */
 };
 
 /* backward flags */
@@ -125,6 +126,44 @@ long long msda_total_launch_count(void);
 enum { MSDA_KERNEL_FORWARD = 1, MSDA_KERNEL_BACKWARD = 2 };
 int msda_profile_enable(int on);
 int msda_profile_collect(float* ms, int* kinds, int max_records);
+
+/*
+ * Fused pre-op (opt-in, `MSDeformAttnFunction.apply` is unchanged).
+ *
+ * These two entry points fold into the sampling kernels the arithmetic upstream `MSDeformAttn.forward`
+ * (maskdino/modeling/pixel_decoder/ops/modules/ms_deform_attn.py) performs between its Linears and
+ * `MSDeformAttnFunction.apply`:
+ *     attention_weights = softmax(attn_logits over L*P)
+ *     sampling_locations = reference_points[:, :, None, :, None, :] + sampling_offsets / (W_l, H_l)      ref_dim == 2
+ *                        = reference_points[..., :2] + sampling_offsets / P * reference_points[..., 2:] * 0.5   ref_dim == 4
+ * with the same fp32 rounding order, so that sampling_locations / attention_weights and their gradients are
+ * never written to or read from HBM (12 of the 20 forward and 24 of the 36 backward algorithmic bytes per
+ * sampled point at the encoder shape).
+ *
+ *   reference_points   (N, Lq, L, ref_dim)   float32
+ *   sampling_offsets   (N, Lq, M, L, P, 2)   float32   raw output of the sampling_offsets Linear
+ *   attn_logits        (N, Lq, M, L*P)       float32   raw output of the attention_weights Linear
+ *
+ * The backward returns the gradients of sampling_offsets and attn_logits (softmax and offset chain rules applied
+ * in shared memory); reference_points receives no gradient here (callers that need one compose the plain operator).
+ * Scratch: msda_backward_scratch_bytes().  Vector kernels only: msda_fused_supported() tells whether (D, dtype)
+ * is covered; otherwise MSDA_ERR_FUSED_UNSUPPORTED is returned and nothing is enqueued.
+ */
+int msda_fused_supported(int D, int value_dtype);
+
+int msda_fused_forward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                       const void* reference_points, int ref_dim, const void* sampling_offsets,
+                       const void* attn_logits, void* output,
+                       int N, int S, int M, int D, int Lq, int L, int P,
+                       int value_dtype, int im2col_step, void* stream);
+
+int msda_fused_backward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                        const void* reference_points, int ref_dim, const void* sampling_offsets,
+                        const void* attn_logits, const void* grad_output,
+                        void* grad_value, void* grad_sampling_offsets, void* grad_attn_logits,
+                        void* scratch, size_t scratch_bytes,
+                        int N, int S, int M, int D, int Lq, int L, int P,
+                        int value_dtype, int im2col_step, int flags, void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,4 +16,6 @@ from .ms_deform_attn_oracle import (  # noqa: F401
     ms_deform_attn_core_pytorch,
     ms_deform_attn_oracle_grads,
     ms_deform_attn_scalar_numpy,
+    msdeformattn_preop_pytorch,
+    ms_deform_attn_fused_oracle_grads,
 )

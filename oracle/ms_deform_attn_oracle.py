@@ -124,3 +124,38 @@ def ms_deform_attn_scalar_numpy(value, value_spatial_shapes, level_start_index, 
     if want_grad:
         return out, gv, gl, ga
     return out
+
+
+def msdeformattn_preop_pytorch(reference_points, sampling_offsets, attention_logits, value_spatial_shapes):
+    """The arithmetic upstream ``MSDeformAttn.forward`` (``modules/ms_deform_attn.py``) performs between its Linears
+    and ``MSDeformAttnFunction.apply``: softmax of the attention logits over L*P, and
+    ``sampling_locations = reference_points[:, :, None, :, None, :] + sampling_offsets / (W_l, H_l)`` for 2-d
+    reference points, ``reference_points[..., :2] + sampling_offsets / P * reference_points[..., 2:] * 0.5`` for
+    4-d reference boxes.  reference_points (N,Lq,L,2|4); sampling_offsets (N,Lq,M,L,P,2); logits (N,Lq,M,L*P)."""
+    N_, Lq_, M_, L_, P_, _ = sampling_offsets.shape
+    attention_weights = F.softmax(attention_logits.reshape(N_, Lq_, M_, L_ * P_), -1).view(N_, Lq_, M_, L_, P_)
+    shapes = torch.as_tensor(_shapes_list(value_spatial_shapes), dtype=torch.long, device=sampling_offsets.device)
+    if reference_points.shape[-1] == 2:
+        offset_normalizer = torch.stack([shapes[..., 1], shapes[..., 0]], -1)
+        sampling_locations = reference_points[:, :, None, :, None, :] \
+            + sampling_offsets / offset_normalizer[None, None, None, :, None, :]
+    elif reference_points.shape[-1] == 4:
+        sampling_locations = reference_points[:, :, None, :, None, :2] \
+            + sampling_offsets / P_ * reference_points[:, :, None, :, None, 2:] * 0.5
+    else:
+        raise ValueError("Last dim of reference_points must be 2 or 4")
+    return sampling_locations, attention_weights
+
+
+def ms_deform_attn_fused_oracle_grads(value, value_spatial_shapes, reference_points, sampling_offsets,
+                                      attention_logits, grad_output, dtype=torch.float64):
+    """Oracle of the opt-in fused operator: pre-op + core, gradients by torch autograd, in ``dtype`` on the CPU.
+    Returns (out, grad_value, grad_sampling_offsets, grad_attention_logits)."""
+    v = value.detach().to("cpu", dtype).requires_grad_(True)
+    ref = reference_points.detach().to("cpu", dtype)
+    off = sampling_offsets.detach().to("cpu", dtype).requires_grad_(True)
+    lg = attention_logits.detach().to("cpu", dtype).requires_grad_(True)
+    loc, aw = msdeformattn_preop_pytorch(ref, off, lg, value_spatial_shapes)
+    out = ms_deform_attn_core_pytorch(v, value_spatial_shapes, loc, aw)
+    out.backward(grad_output.detach().to("cpu", dtype))
+    return out.detach(), v.grad, off.grad, lg.grad

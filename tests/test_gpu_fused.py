@@ -1,0 +1,208 @@
+"""GPU parity of the opt-in fused pre-op: ``MSDeformAttnFusedFunction`` — softmax over L*P and
+``reference_points (+) sampling_offsets`` folded into the kernels — against the CPU oracle of the same composition
+(``oracle.msdeformattn_preop_pytorch`` + ``ms_deform_attn_core_pytorch``), and against the plain operator fed with
+torch-materialised sampling locations / attention weights.  Tolerances as for the plain operator: 1e-5 relative in
+fp32, 2e-2 in bf16 (relative = max-abs error / max-abs of the oracle tensor)."""
+import pytest
+import torch
+
+from oracle import ms_deform_attn_fused_oracle_grads, msdeformattn_preop_pytorch
+from tests.helpers import lsi_of, rel_to_max
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-5, torch.bfloat16: 2e-2, torch.float16: 5e-3}
+
+
+@pytest.fixture(scope="module")
+def ops(built_library):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import vision_instance_seg_b200 as pkg
+    pkg.load_library()
+    return pkg
+
+
+def fused_problem(N, M, D, Lq, shapes, P, ref_dim, seed=0, offset_scale=2.0):
+    g = torch.Generator().manual_seed(seed)
+    ss = torch.as_tensor(shapes, dtype=torch.long)
+    S = int(ss.prod(1).sum())
+    L = len(shapes)
+    value = torch.randn(N, S, M, D, generator=g)
+    if ref_dim == 2:
+        ref = torch.rand(N, Lq, L, 2, generator=g) * 1.1 - 0.05
+    else:
+        ref = torch.cat([torch.rand(N, Lq, L, 2, generator=g), torch.rand(N, Lq, L, 2, generator=g) * 0.6 + 0.02], -1)
+    off = torch.randn(N, Lq, M, L, P, 2, generator=g) * offset_scale
+    logits = torch.randn(N, Lq, M, L * P, generator=g) * 2.0
+    grad_out = torch.randn(N, Lq, M * D, generator=g)
+    return value, ss, lsi_of(ss), ref, off, logits, grad_out
+
+
+def run_fused(ops, problem, dtype):
+    value, ss, lsi, ref, off, logits, go = problem
+    dev = torch.device("cuda:0")
+    v = value.to(dev, dtype).requires_grad_(True)
+    o = off.to(dev).requires_grad_(True)
+    lg = logits.to(dev).requires_grad_(True)
+    out = ops.MSDeformAttnFusedFunction.apply(v, ss.to(dev), lsi.to(dev), ref.to(dev), o, lg, 64)
+    out.backward(go.to(dev, dtype))
+    torch.cuda.synchronize()
+    return out.detach(), v.grad, o.grad, lg.grad
+
+
+def check_fused(ops, problem, dtype):
+    value, ss, lsi, ref, off, logits, go = problem
+    got = run_fused(ops, problem, dtype)
+    want = ms_deform_attn_fused_oracle_grads(value.to(dtype).double(), ss, ref.double(), off.double(), logits.double(),
+                                             go.to(dtype).double())
+    for name, g, w in zip(("out", "grad_value", "grad_offsets", "grad_logits"), got, want):
+        err = rel_to_max(g, w)
+        assert err < TOL[dtype], f"{name} ({dtype}, ref_dim {ref.shape[-1]}): rel-to-max error {err:.3e} >= {TOL[dtype]}"
+    assert got[0].dtype == dtype and got[1].dtype == dtype and got[2].dtype == torch.float32 and got[3].dtype == torch.float32
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_fused_matches_oracle_encoder_like(ops, ref_dim, dtype):
+    check_fused(ops, fused_problem(2, 8, 32, 77, [(16, 12), (8, 6), (4, 3)], 4, ref_dim, seed=ref_dim), dtype)
+
+
+@pytest.mark.parametrize("D", [16, 32, 64, 128])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_all_vector_head_dims(ops, D, dtype):
+    # M = 3 and Lq = 5: pairs straddle queries inside a warp and the last warp is ragged
+    check_fused(ops, fused_problem(1, 3, D, 5, [(7, 9), (4, 4)], 3, 2, seed=D), dtype)
+
+
+@pytest.mark.parametrize("LP", [(1, 1), (2, 3), (4, 4), (5, 2)])
+def test_fused_level_point_counts(ops, LP):
+    L, P = LP
+    shapes = [(9, 7), (5, 4), (3, 3), (2, 2), (6, 6)][:L]
+    for ref_dim in (2, 4):
+        check_fused(ops, fused_problem(2, 4, 32, 11, shapes, P, ref_dim, seed=L * 10 + P), torch.float32)
+
+
+def test_fused_equals_plain_operator_on_materialised_inputs(ops):
+    """Same kernels behind both entry points: with sampling locations / attention weights materialised by torch on the
+    GPU (what the unfused module does), the plain operator must agree with the fused one to fp32 rounding."""
+    dev = "cuda:0"
+    for ref_dim in (2, 4):
+        value, ss, lsi, ref, off, logits, go = fused_problem(2, 8, 32, 301, [(32, 32), (16, 16), (8, 8), (4, 4)], 4, ref_dim, seed=5)
+        v1 = value.to(dev).requires_grad_(True)
+        o1 = off.to(dev).requires_grad_(True)
+        l1 = logits.to(dev).requires_grad_(True)
+        out1 = ops.MSDeformAttnFusedFunction.apply(v1, ss.to(dev), lsi.to(dev), ref.to(dev), o1, l1, 64)
+        out1.backward(go.to(dev))
+        v2 = value.to(dev).requires_grad_(True)
+        o2 = off.to(dev).requires_grad_(True)
+        l2 = logits.to(dev).requires_grad_(True)
+        N, Lq, M, L, P, _ = off.shape
+        aw = torch.softmax(l2, -1).view(N, Lq, M, L, P)
+        ssd = ss.to(dev)
+        if ref_dim == 2:
+            norm = torch.stack([ssd[..., 1], ssd[..., 0]], -1)
+            loc = ref.to(dev)[:, :, None, :, None, :] + o2 / norm[None, None, None, :, None, :]
+        else:
+            r = ref.to(dev)
+            loc = r[:, :, None, :, None, :2] + o2 / P * r[:, :, None, :, None, 2:] * 0.5
+        out2 = ops.MSDeformAttnFunction.apply(v2, ssd, lsi.to(dev), loc, aw, 64)
+        out2.backward(go.to(dev))
+        torch.cuda.synchronize()
+        for name, a, b in (("out", out1, out2), ("grad_value", v1.grad, v2.grad), ("grad_offsets", o1.grad, o2.grad),
+                           ("grad_logits", l1.grad, l2.grad)):
+            assert rel_to_max(a, b) < 2e-6, f"{name} (ref_dim {ref_dim})"
+
+
+def test_fused_full_size_encoder_shape_properties(ops):
+    """cfg3 geometry (1024^2 -> 128/64/32/16, 21 760 queries, bf16) at N = 2: the oracle would need minutes, so the fused
+    path is checked through the plain operator (bit-equal forward when fed torch-materialised operands whose rounding
+    agrees) and through a size-independent property: logits shifted by a per-pair constant leave every result unchanged."""
+    from vision_instance_seg_b200 import workloads as W
+    dev = torch.device("cuda:0")
+    shapes = W.CONFIGS["cfg3_swinl_1024_bf16"]["shapes"]
+    ss = W.make_spatial_shapes(shapes, dev)
+    lsi = W.make_level_start_index(ss)
+    S = int(ss.prod(1).sum())
+    N, M, D, L, P = 2, 8, 32, 4, 4
+    g = torch.Generator(device=dev).manual_seed(11)
+    value = torch.randn(N, S, M, D, generator=g, device=dev).to(torch.bfloat16)
+    ref = W.get_reference_points(ss, torch.ones(N, L, 2, device=dev), dev).contiguous()
+    off = torch.randn(N, S, M, L, P, 2, generator=g, device=dev) * 2.0
+    logits = torch.randn(N, S, M, L * P, generator=g, device=dev)
+    go = torch.randn(N, S, M * D, generator=g, device=dev).to(torch.bfloat16)
+
+    def run(lg):
+        v = value.clone().requires_grad_(True)
+        o = off.clone().requires_grad_(True)
+        l_ = lg.clone().requires_grad_(True)
+        out = ops.MSDeformAttnFusedFunction.apply(v, ss, lsi, ref, o, l_, 128)
+        out.backward(go)
+        return out.detach(), v.grad, o.grad, l_.grad
+
+    base = run(logits)
+    loc, aw = msdeformattn_preop_pytorch(ref, off, logits, ss.cpu())       # torch on the GPU, the module's expressions
+    v2 = value.clone().requires_grad_(True)
+    out2 = ops.MSDeformAttnFunction.apply(v2, ss, lsi, loc.contiguous(), aw.contiguous(), 128)
+    out2.backward(go)
+    torch.cuda.synchronize()
+    assert rel_to_max(base[0], out2) < 1e-2          # bf16 outputs; softmax may differ in the last fp32 ulp
+    assert rel_to_max(base[1], v2.grad) < 2e-2
+    shift = torch.randn(N, S, M, 1, generator=g, device=dev).mul(3).round()     # softmax is shift-invariant per pair
+    shifted = run(logits + shift)
+    for name, a, b in zip(("out", "grad_value", "grad_offsets", "grad_logits"), base, shifted):
+        assert rel_to_max(a, b) < 1e-2, name
+    assert float(base[3].sum(-1).abs().max()) < 1e-3 * float(base[3].abs().max()) + 1e-6   # softmax grads sum to 0 per pair
+
+
+def test_fused_rejects_unsupported_and_reference_grad(ops):
+    dev = "cuda:0"
+    value, ss, lsi, ref, off, logits, go = fused_problem(1, 2, 30, 4, [(5, 5)], 2, 2)
+    with pytest.raises(RuntimeError):       # D = 30 is served by the compatibility kernels only
+        ops.MSDeformAttnFusedFunction.apply(value.to(dev), ss.to(dev), lsi.to(dev), ref.to(dev), off.to(dev), logits.to(dev), 64)
+    value, ss, lsi, ref, off, logits, go = fused_problem(1, 2, 32, 4, [(5, 5)], 2, 2)
+    r = ref.to(dev).requires_grad_(True)
+    out = ops.MSDeformAttnFusedFunction.apply(value.to(dev), ss.to(dev), lsi.to(dev), r, off.to(dev).requires_grad_(True),
+                                              logits.to(dev), 64)
+    with pytest.raises(RuntimeError):
+        out.sum().backward()
+    assert not ops.MultiScaleDeformableAttention.fused_supported(value.double().to(dev), ref.to(dev))
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_module_fused_flag_matches_unfused(ops, ref_dim):
+    from vision_instance_seg_b200 import workloads as W
+    torch.manual_seed(3 + ref_dim)
+    shapes = [(20, 16), (10, 8), (5, 4)]
+    ss = W.make_spatial_shapes(shapes).cuda()
+    lsi = W.make_level_start_index(ss)
+    S = int(ss.prod(1).sum())
+    N = 2
+    m = ops.MSDeformAttn(d_model=256, n_levels=3, n_heads=8, n_points=4).cuda()
+    with torch.no_grad():
+        m.sampling_offsets.weight.normal_(0, 0.02)
+        m.attention_weights.weight.normal_(0, 0.3)
+    src = torch.randn(N, S, 256, device="cuda")
+    if ref_dim == 2:
+        query = src + 0.1 * torch.randn_like(src)
+        ref = W.get_reference_points(ss, torch.ones(N, 3, 2, device="cuda"), "cuda")
+    else:
+        query = torch.randn(N, 50, 256, device="cuda")
+        ref = torch.cat([torch.rand(N, 50, 1, 2, device="cuda").expand(-1, -1, 3, -1),
+                         torch.rand(N, 50, 1, 2, device="cuda").expand(-1, -1, 3, -1) * 0.4 + 0.05], -1)
+    res = []
+    for fused in (False, True):
+        assert ops.set_fused_preop(m, fused) == 1
+        m.zero_grad()
+        q = query.clone().requires_grad_(True)
+        s = src.clone().requires_grad_(True)
+        out = m(q, ref, s, ss, lsi)
+        out.square().sum().backward()
+        res.append((out.detach(), q.grad, s.grad, m.sampling_offsets.weight.grad.clone(), m.attention_weights.weight.grad.clone(),
+                    m.value_proj.weight.grad.clone()))
+    for a, b in zip(*res):
+        assert rel_to_max(a, b) < 1e-5
+    # reference points that require grad: the module composes the plain operator (fused op has no grad for them)
+    ops.set_fused_preop(m, True)
+    r = ref.clone().requires_grad_(True)
+    m(query, r, src, ss, lsi).sum().backward()
+    assert r.grad is not None and torch.isfinite(r.grad).all()

@@ -73,3 +73,7 @@ if __name__ == "__main__":
     timing("cfg3_fp32", W.make_encoder_inputs, torch.float32, shapes=c3, batch=16)
     timing("cfg3_uniform", W.make_uniform_inputs, torch.bfloat16, shapes=c3, batch=16)
     timing("cfg4_dec", W.make_decoder_inputs, torch.bfloat16, shapes=c3, batch=16)
+    timing("cfg4_dec_500q", W.make_decoder_inputs, torch.bfloat16, shapes=c3, batch=16, queries=500)
+    c5 = W.CONFIGS["cfg5_2048_bf16"]["shapes"]
+    for nb in (16, 8, 4, 2):
+        timing(f"cfg5_n{nb}", W.make_encoder_inputs, torch.bfloat16, shapes=c5, batch=nb)

@@ -115,3 +115,92 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     if grad_attn.dtype != attn_weight.dtype:
         grad_attn = grad_attn.to(attn_weight.dtype)
     return [grad_value, grad_loc, grad_attn]
+
+
+# ---------------------------------------------------------------------------------------------------
+# Fused pre-op (opt-in).  Not part of the upstream extension: the two functions below fold
+# the softmax over L*P and the sampling-location arithmetic of upstream ``MSDeformAttn.forward`` into the kernels.
+# ---------------------------------------------------------------------------------------------------
+def fused_supported(value: torch.Tensor, reference_points: torch.Tensor) -> bool:
+    """True when the fused kernels cover this call (vector kernels: head dim 16/32/64/128, fp32/bf16/fp16
+    values; reference points of width 2 or 4)."""
+    if value.dtype not in _DTYPES or value.dim() != 4 or reference_points.shape[-1] not in (2, 4):
+        return False
+    return bool(_lib.load_library().msda_fused_supported(int(value.shape[-1]), _DTYPES[value.dtype]))
+
+
+def _fused_dims(value, spatial_shapes, reference_points, sampling_offsets, attn_logits):
+    if value.dim() != 4 or sampling_offsets.dim() != 6 or reference_points.dim() != 4:
+        raise RuntimeError("value must be (N, S, M, D), sampling_offsets (N, Lq, M, L, P, 2), reference_points (N, Lq, L, 2|4)")
+    N, S, M, D = value.shape
+    N2, Lq, M2, L, P, two = sampling_offsets.shape
+    if (M2 != M or two != 2 or N2 != N or spatial_shapes.shape[0] != L or attn_logits.numel() != N * Lq * M * L * P
+            or tuple(reference_points.shape[:3]) != (N, Lq, L) or reference_points.shape[3] not in (2, 4)):
+        raise RuntimeError("inconsistent shapes between value, spatial_shapes, reference_points, sampling_offsets and attn_logits")
+    return N, S, M, D, Lq, L, P, int(reference_points.shape[3])
+
+
+def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                 attn_logits, im2col_step):
+    """output = MSDeformAttn core applied to softmax(attn_logits) and reference_points (+) sampling_offsets."""
+    for t, n in ((value, "value"), (spatial_shapes, "spatial_shapes"), (level_start_index, "level_start_index"),
+                 (reference_points, "reference_points"), (sampling_offsets, "sampling_offsets"), (attn_logits, "attn_logits")):
+        _require(t, n)
+    if value.dtype not in _DTYPES:
+        raise RuntimeError(f"ms_deform_attn_fused_forward not implemented for '{value.dtype}'")
+    N, S, M, D, Lq, L, P, R = _fused_dims(value, spatial_shapes, reference_points, sampling_offsets, attn_logits)
+    ref = reference_points if reference_points.dtype == torch.float32 else reference_points.float()
+    off = sampling_offsets if sampling_offsets.dtype == torch.float32 else sampling_offsets.float()
+    logits = attn_logits if attn_logits.dtype == torch.float32 else attn_logits.float()
+    shapes = _meta(spatial_shapes, value.device)
+    lsi = _meta(level_start_index, value.device)
+    lib = _lib.load_library()
+    with torch.cuda.device(value.device):
+        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        if out.numel() == 0:
+            return out
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = lib.msda_fused_forward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), ref.data_ptr(), R, off.data_ptr(),
+                                    logits.data_ptr(), out.data_ptr(), N, S, M, D, Lq, L, P, _DTYPES[value.dtype],
+                                    int(im2col_step), stream)
+    _lib.check(rc, "ms_deform_attn_fused_forward")
+    return out
+
+
+def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                  attn_logits, grad_output, im2col_step):
+    """-> [grad_value, grad_sampling_offsets, grad_attn_logits] (reference_points gets no gradient here)."""
+    for t, n in ((value, "value"), (spatial_shapes, "spatial_shapes"), (level_start_index, "level_start_index"),
+                 (reference_points, "reference_points"), (sampling_offsets, "sampling_offsets"), (attn_logits, "attn_logits"),
+                 (grad_output, "grad_output")):
+        _require(t, n)
+    if value.dtype not in _DTYPES:
+        raise RuntimeError(f"ms_deform_attn_fused_backward not implemented for '{value.dtype}'")
+    N, S, M, D, Lq, L, P, R = _fused_dims(value, spatial_shapes, reference_points, sampling_offsets, attn_logits)
+    ref = reference_points if reference_points.dtype == torch.float32 else reference_points.float()
+    off = sampling_offsets if sampling_offsets.dtype == torch.float32 else sampling_offsets.float()
+    logits = attn_logits if attn_logits.dtype == torch.float32 else attn_logits.float()
+    go = grad_output if grad_output.dtype == value.dtype else grad_output.to(value.dtype)
+    shapes = _meta(spatial_shapes, value.device)
+    lsi = _meta(level_start_index, value.device)
+    lib = _lib.load_library()
+    code = _DTYPES[value.dtype]
+    with torch.cuda.device(value.device):
+        grad_value = torch.empty_like(value)
+        grad_off = torch.empty(sampling_offsets.shape, dtype=torch.float32, device=value.device)
+        grad_logits = torch.empty(attn_logits.shape, dtype=torch.float32, device=value.device)
+        if grad_off.numel() == 0 or value.numel() == 0:
+            return [grad_value.zero_(), grad_off.zero_(), grad_logits.zero_()]
+        nbytes = lib.msda_backward_scratch_bytes(N, S, M, D, Lq, L, P, code, backward_flags)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=value.device) if nbytes else None
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = lib.msda_fused_backward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), ref.data_ptr(), R, off.data_ptr(),
+                                     logits.data_ptr(), go.data_ptr(), grad_value.data_ptr(), grad_off.data_ptr(),
+                                     grad_logits.data_ptr(), scratch.data_ptr() if scratch is not None else None, nbytes,
+                                     N, S, M, D, Lq, L, P, code, int(im2col_step), backward_flags, stream)
+    _lib.check(rc, "ms_deform_attn_fused_backward")
+    if grad_off.dtype != sampling_offsets.dtype:
+        grad_off = grad_off.to(sampling_offsets.dtype)
+    if grad_logits.dtype != attn_logits.dtype:
+        grad_logits = grad_logits.to(attn_logits.dtype)
+    return [grad_value, grad_off, grad_logits]

@@ -18,7 +18,8 @@ the built library or without a CUDA device raises.
 """
 from . import MultiScaleDeformableAttention  # noqa: F401
 from ._lib import library_path, load_library  # noqa: F401
-from .functions import MSDeformAttnFunction  # noqa: F401
-from .modules import MSDeformAttn  # noqa: F401
+from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction  # noqa: F401
+from .modules import MSDeformAttn, set_fused_preop  # noqa: F401
 
-__all__ = ["MSDeformAttn", "MSDeformAttnFunction", "MultiScaleDeformableAttention", "load_library", "library_path"]
+__all__ = ["MSDeformAttn", "MSDeformAttnFunction", "MSDeformAttnFusedFunction", "MultiScaleDeformableAttention",
+           "set_fused_preop", "load_library", "library_path"]

@@ -35,6 +35,9 @@ EXPORTED_SYMBOLS = (
     "msda_total_launch_count",
     "msda_profile_enable",
     "msda_profile_collect",
+    "msda_fused_supported",
+    "msda_fused_forward",
+    "msda_fused_backward",
 )
 
 
@@ -57,6 +60,13 @@ def _declare(lib):
     lib.msda_backward.restype = i
     lib.msda_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, vp, vp, vp, vp, sz,
                                   i, i, i, i, i, i, i, i, i, i, vp]
+    lib.msda_fused_supported.restype = i
+    lib.msda_fused_supported.argtypes = [i, i]
+    lib.msda_fused_forward.restype = i
+    lib.msda_fused_forward.argtypes = [vp, i64p, i64p, vp, i, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]
+    lib.msda_fused_backward.restype = i
+    lib.msda_fused_backward.argtypes = [vp, i64p, i64p, vp, i, vp, vp, vp, vp, vp, vp, vp, sz,
+                                        i, i, i, i, i, i, i, i, i, i, vp]
     lib.msda_total_launch_count.restype = ctypes.c_longlong
     lib.msda_total_launch_count.argtypes = []
     lib.msda_profile_enable.restype = i

@@ -40,6 +40,7 @@ namespace msda {
 struct WarpStage {
   float* loc;        // [GPW][2*LP + 4]
   float* attn;       // [GPW][LP + 4]
+  float* gattn;      // [GPW][LP + 4]  fused backward only: grad wrt the softmax output (attn itself is kept)
   int loc_stride, attn_stride;
 };
 
@@ -67,7 +68,8 @@ __device__ __forceinline__ void stage_in(const WarpStage& ws, const float* __res
   }
 }
 
-__device__ __forceinline__ void stage_out(const WarpStage& ws, float* __restrict__ gl, float* __restrict__ ga,
+__device__ __forceinline__ void stage_out(const WarpStage& ws, const float* __restrict__ attn_src,
+                                          float* __restrict__ gl, float* __restrict__ ga,
                                           int nvalid, int LP, int lane) {
   if ((LP & 3) == 0) {
     const int lv = LP / 2, av = LP / 4;
@@ -77,7 +79,7 @@ __device__ __forceinline__ void stage_out(const WarpStage& ws, float* __restrict
     }
     for (int i = lane; i < nvalid * av; i += 32) {
       const int r = i / av, k = i - r * av;
-      __stcs(reinterpret_cast<float4*>(ga) + i, *reinterpret_cast<const float4*>(ws.attn + r * ws.attn_stride + 4 * k));
+      __stcs(reinterpret_cast<float4*>(ga) + i, *reinterpret_cast<const float4*>(attn_src + r * ws.attn_stride + 4 * k));
     }
   } else {
     for (int i = lane; i < nvalid * 2 * LP; i += 32) {
@@ -86,19 +88,86 @@ __device__ __forceinline__ void stage_out(const WarpStage& ws, float* __restrict
     }
     for (int i = lane; i < nvalid * LP; i += 32) {
       const int r = i / LP, k = i - r * LP;
-      ga[i] = ws.attn[r * ws.attn_stride + k];
+      ga[i] = attn_src[r * ws.attn_stride + k];
     }
   }
 }
 
 // =====================================================================================================
+// Fused pre-op.  In fused mode the kernels consume what MSDeformAttn.forward holds
+// *before* it materialises sampling_locations / softmaxed attention_weights: the raw outputs of the
+// sampling_offsets and attention_weights Linears plus reference_points (N, Lq, L, R), R = 2 (encoder: points)
+// or 4 (decoder: boxes).  After the warp's rows are staged, each lane group rewrites its own row in place,
+// with the module's arithmetic and rounding order:
+//     R == 2:  loc = ref + off / (W_l, H_l)                       (fp32 division, then add)
+//     R == 4:  loc = ref_xy + ((off / P) * ref_wh) * 0.5
+//     attn = softmax over the L*P logits of the pair = exp(x - max) / sum
+// The backward applies the matching chain rules to grad_loc / grad_attn before they leave shared memory:
+//     R == 2:  grad_off = grad_loc / (W_l, H_l);   R == 4:  grad_off = ((grad_loc * 0.5) * ref_wh) / P
+//     grad_logit = (grad_attn - sum_j(grad_attn_j * attn_j)) * attn
+// so sampling_locations / attention_weights and their gradients never exist in HBM.
+// =====================================================================================================
+template <int G>
+__device__ __forceinline__ unsigned group_mask(int g) {
+  if constexpr (G >= 32) return 0xffffffffu;
+  else return ((1u << G) - 1u) << (g * G);
+}
+
+template <int G>
+__device__ __forceinline__ void fused_prepare(float* myloc, float* myattn, const LevelMeta& meta,
+                                              const float* __restrict__ refq, int R, int L, int P, int c, unsigned gmask) {
+  const int LP = L * P;
+  const float Pf = static_cast<float>(P);
+  for (int i = c; i < LP; i += G) {
+    const int l = i / P;
+    const float2 off = *reinterpret_cast<const float2*>(myloc + 2 * i);
+    float x, y;
+    if (R == 2) {
+      const float2 r = __ldg(reinterpret_cast<const float2*>(refq) + l);
+      x = __fadd_rn(r.x, __fdiv_rn(off.x, static_cast<float>(meta.W[l])));
+      y = __fadd_rn(r.y, __fdiv_rn(off.y, static_cast<float>(meta.H[l])));
+    } else {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(refq) + l);
+      x = __fadd_rn(r.x, __fmul_rn(__fmul_rn(__fdiv_rn(off.x, Pf), r.z), 0.5f));
+      y = __fadd_rn(r.y, __fmul_rn(__fmul_rn(__fdiv_rn(off.y, Pf), r.w), 0.5f));
+    }
+    *reinterpret_cast<float2*>(myloc + 2 * i) = make_float2(x, y);
+  }
+  float mx = -INFINITY;
+  for (int i = c; i < LP; i += G) mx = fmaxf(mx, myattn[i]);
+#pragma unroll
+  for (int s = G / 2; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, s));
+  float sum = 0.f;
+  for (int i = c; i < LP; i += G) {
+    const float e = expf(__fsub_rn(myattn[i], mx));
+    myattn[i] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int s = G / 2; s >= 1; s >>= 1) sum += __shfl_xor_sync(gmask, sum, s);
+  for (int i = c; i < LP; i += G) myattn[i] = __fdiv_rn(myattn[i], sum);
+  __syncwarp(gmask);
+}
+
+// grad_loc of point i (level l) -> grad of the raw sampling offset
+__device__ __forceinline__ float2 fused_offset_grad(float gx, float gy, const LevelMeta& meta, const float* __restrict__ refq,
+                                                    int R, int l, int P) {
+  if (R == 2)
+    return make_float2(__fdiv_rn(gx, static_cast<float>(meta.W[l])), __fdiv_rn(gy, static_cast<float>(meta.H[l])));
+  const float4 r = __ldg(reinterpret_cast<const float4*>(refq) + l);
+  const float Pf = static_cast<float>(P);
+  return make_float2(__fdiv_rn(__fmul_rn(__fmul_rn(gx, 0.5f), r.z), Pf), __fdiv_rn(__fmul_rn(__fmul_rn(gy, 0.5f), r.w), Pf));
+}
+
+// =====================================================================================================
 // Forward, vector path
 // =====================================================================================================
-template <typename T, int D>
+// FUSED: `loc` / `attn` hold raw sampling offsets / attention logits and `ref` (N, Lq, L, R) the reference points
+template <typename T, int D, bool FUSED>
 __global__ void __launch_bounds__(kThreads)
 msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
-                    const float* __restrict__ attn, T* __restrict__ out,
+                    const float* __restrict__ attn, const float* __restrict__ ref, int R, T* __restrict__ out,
                     int S, int M, int Lq, int L, int P, int total_pairs) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr int G = D / VEC;        // lanes per (b, q, m) pair
@@ -117,6 +186,7 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   ws.attn_stride = LP + 4;
   ws.loc = smem + warp * GPW * (ws.loc_stride + ws.attn_stride);
   ws.attn = ws.loc + GPW * ws.loc_stride;
+  ws.gattn = nullptr;
 
   const int pair0 = (blockIdx.x * kWarps + warp) * GPW;
   const int nvalid = min(GPW, total_pairs - pair0);
@@ -130,8 +200,10 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   const int b = (pair / M) / Lq;
   const uint32_t pix_bytes = static_cast<uint32_t>(M) * D * sizeof(T);        // bytes between neighbouring pixels
   const char* vb = reinterpret_cast<const char*>(value) + (static_cast<size_t>(b) * S * M + m) * (D * sizeof(T)) + c * 16;
-  const float* myloc = ws.loc + g * ws.loc_stride;
-  const float* myattn = ws.attn + g * ws.attn_stride;
+  float* myloc = ws.loc + g * ws.loc_stride;
+  float* myattn = ws.attn + g * ws.attn_stride;
+  if constexpr (FUSED)
+    fused_prepare<G>(myloc, myattn, meta, ref + static_cast<size_t>(pair / M) * L * R, R, L, P, c, group_mask<G>(g));
 
   float acc[VEC];
 #pragma unroll
@@ -202,11 +274,14 @@ __device__ __forceinline__ float f16_accum_scale(const uint32_t* __restrict__ ct
 // GV16 = true : 16-bit T only; contributions are scaled (f16_accum_scale), rounded to fp16 and added with
 //               packed red.global.add.noftz.v4.f16x2 into an fp16 buffer `gv16` laid out like value: half the
 //               reduction bytes of the fp32 path (the SM->L2 reduction path is what bounds this kernel).
-template <typename T, int D, bool GV16>
+// FUSED   : `loc` / `attn` hold raw sampling offsets / attention logits, `ref` (N, Lq, L, R) the reference points;
+//           `grad_loc` / `grad_attn` receive the gradients of the raw offsets / logits (see fused_prepare).
+template <typename T, int D, bool GV16, bool FUSED>
 __global__ void __launch_bounds__(kThreads, BWD_MIN_CTAS)
 msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
-                    const float* __restrict__ attn, const T* __restrict__ grad_out,
+                    const float* __restrict__ attn, const float* __restrict__ ref, int R,
+                    const T* __restrict__ grad_out,
                     float* __restrict__ gv32, __half* __restrict__ gv16, const uint32_t* __restrict__ ctrl,
                     float* __restrict__ grad_loc, float* __restrict__ grad_attn,
                     int S, int M, int Lq, int L, int P, int total_pairs, int depth) {
@@ -228,8 +303,9 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   WarpStage ws;
   ws.loc_stride = 2 * LP + 4;
   ws.attn_stride = LP + 4;
-  ws.loc = smem + warp * GPW * (ws.loc_stride + ws.attn_stride);
+  ws.loc = smem + warp * GPW * (ws.loc_stride + (FUSED ? 2 : 1) * ws.attn_stride);
   ws.attn = ws.loc + GPW * ws.loc_stride;
+  ws.gattn = FUSED ? ws.attn + GPW * ws.attn_stride : nullptr;
 
   const int pair0 = (blockIdx.x * kWarps + warp) * GPW;
   const int nvalid = min(GPW, total_pairs - pair0);
@@ -248,6 +324,15 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   const char* vb = reinterpret_cast<const char*>(value) + img_pix * (D * sizeof(T)) + c * 16;
   float* myloc = ws.loc + (active ? g : 0) * ws.loc_stride;
   float* myattn = ws.attn + (active ? g : 0) * ws.attn_stride;
+  float* mygattn = nullptr;
+  const float* refq = nullptr;
+  if constexpr (FUSED) {
+    mygattn = ws.gattn + (active ? g : 0) * ws.attn_stride;
+    refq = ref + static_cast<size_t>(pair / M) * L * R;
+    // padding groups shadow row 0 read-only: only the owning group rewrites a row
+    if (active) fused_prepare<G>(myloc, myattn, meta, refq, R, L, P, c, group_mask<G>(g));
+    __syncwarp();
+  }
 
   // grad_out of this pair: raw 16 bytes in the value layout (for the dot products) and, for the fp32
   // scatter of 16-bit types, the fp32 values of the channels this lane adds: lanes of a group then cover
@@ -363,12 +448,31 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     // the owner lane now holds the group totals of point lp0 + owner; every lane of the group has already
     // read that point's (x, y, attn), so the gradients can replace them in place
     if (active && owner >= 0 && lp0 + owner < LP) {
-      *reinterpret_cast<float2*>(myloc + 2 * (lp0 + owner)) = make_float2(part[0][1], part[0][2]);
-      myattn[lp0 + owner] = part[0][0];
+      if constexpr (FUSED) {
+        const int lpo = lp0 + owner;
+        *reinterpret_cast<float2*>(myloc + 2 * lpo) = fused_offset_grad(part[0][1], part[0][2], meta, refq, R, lpo / P, P);
+        mygattn[lpo] = part[0][0];        // the softmax output stays in myattn for the chain rule below
+      } else {
+        *reinterpret_cast<float2*>(myloc + 2 * (lp0 + owner)) = make_float2(part[0][1], part[0][2]);
+        myattn[lp0 + owner] = part[0][0];
+      }
     }
   }
   __syncwarp();
-  stage_out(ws, grad_loc + static_cast<size_t>(pair0) * (2 * LP), grad_attn + static_cast<size_t>(pair0) * LP, nvalid, LP, lane);
+  if constexpr (FUSED) {
+    if (active) {                         // softmax backward over the pair's L*P entries
+      const unsigned gmask = group_mask<G>(g);
+      float dot = 0.f;
+      for (int i = c; i < LP; i += G) dot += mygattn[i] * myattn[i];
+#pragma unroll
+      for (int s = G / 2; s >= 1; s >>= 1) dot += __shfl_xor_sync(gmask, dot, s);
+      for (int i = c; i < LP; i += G) mygattn[i] = __fmul_rn(__fsub_rn(mygattn[i], dot), myattn[i]);
+    }
+    __syncwarp();
+    stage_out(ws, ws.gattn, grad_loc + static_cast<size_t>(pair0) * (2 * LP), grad_attn + static_cast<size_t>(pair0) * LP, nvalid, LP, lane);
+  } else {
+    stage_out(ws, ws.attn, grad_loc + static_cast<size_t>(pair0) * (2 * LP), grad_attn + static_cast<size_t>(pair0) * LP, nvalid, LP, lane);
+  }
 }
 
 // fp32 accumulation buffer -> 16-bit grad_value (one rounding per element)
@@ -399,6 +503,21 @@ msda_absmax_kernel(const T* __restrict__ x, size_t n8, uint32_t* __restrict__ ct
 #pragma unroll
   for (int s = 16; s >= 1; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(ctrl, __float_as_uint(m));
+}
+
+// zero the control block and the rows of the bucketed fp16 accumulator that the device-side layout actually uses
+// (the host only knows the upper bound accum_rows_bound(); for few queries the layout is ~half of it)
+__global__ void __launch_bounds__(256)
+msda_zero_f16_buckets_kernel(uint4* __restrict__ scratch, size_t ctrl_vecs, const int64_t* __restrict__ shapes,
+                             const int64_t* __restrict__ lsi, int N, int M, int D, int Lq, int L, int P, int depth) {
+  __shared__ LevelMeta meta;
+  load_level_meta(meta, shapes, lsi, L);
+  build_accum_layout(meta, L, Lq, P, depth);
+  const size_t total = ctrl_vecs + static_cast<size_t>(N) * meta.accStride * (static_cast<size_t>(M) * D / 8);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    scratch[i] = z;
 }
 
 // bucketed, scaled fp16 accumulation buffer -> 16-bit grad_value: sum the K_l copies in fp32, unscale, round once
@@ -594,6 +713,8 @@ struct ScopedKernelTimer {
 struct Problem {
   int N, S, M, D, Lq, L, P;
   int total_pairs;
+  const float* ref = nullptr;   // fused pre-op: reference points (N, Lq, L, R); nullptr = plain operator
+  int R = 0;
 };
 
 static int validate(const Problem& pr, int dtype, int im2col_step) {
@@ -618,10 +739,10 @@ template <typename T> static bool vec_supported(const Problem& pr) {
 }
 
 template <typename T, int D>
-static size_t vec_smem_bytes(int L, int P) {
+static size_t vec_smem_bytes(int L, int P, bool fused_bwd = false) {
   constexpr int G = D / (16 / static_cast<int>(sizeof(T)));
   constexpr int GPW = 32 / G;
-  return static_cast<size_t>(kWarps) * GPW * (3 * L * P + 8) * sizeof(float);
+  return static_cast<size_t>(kWarps) * GPW * ((fused_bwd ? 4 : 3) * L * P + (fused_bwd ? 12 : 8)) * sizeof(float);
 }
 
 template <typename K>
@@ -630,22 +751,29 @@ static cudaError_t allow_smem(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
 }
 
-template <typename T, int D>
-static int launch_fwd_vec(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
-                          const void* loc, const void* attn, void* out, cudaStream_t st) {
+template <typename T, int D, bool FUSED>
+static int launch_fwd_vec_impl(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
+                               const void* loc, const void* attn, void* out, cudaStream_t st) {
   constexpr int GPW = 32 / (D / (16 / static_cast<int>(sizeof(T))));
   const int per_cta = kWarps * GPW;
   const int grid = (pr.total_pairs + per_cta - 1) / per_cta;
   const size_t smem = vec_smem_bytes<T, D>(pr.L, pr.P);
   if (smem > 200 * 1024) return MSDA_ERR_BAD_SHAPE;
-  cudaError_t e = allow_smem(msda_fwd_vec_kernel<T, D>, smem);
+  cudaError_t e = allow_smem(msda_fwd_vec_kernel<T, D, FUSED>, smem);
   if (e != cudaSuccess) return static_cast<int>(e);
   ScopedKernelTimer timer(MSDA_KERNEL_FORWARD, st);
-  msda_fwd_vec_kernel<T, D><<<grid, kThreads, smem, st>>>(
+  msda_fwd_vec_kernel<T, D, FUSED><<<grid, kThreads, smem, st>>>(
       static_cast<const T*>(value), shapes, lsi, static_cast<const float*>(loc), static_cast<const float*>(attn),
-      static_cast<T*>(out), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs);
+      pr.ref, pr.R, static_cast<T*>(out), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs);
   ++g_last_launches, ++g_total_launches;
   return static_cast<int>(cudaGetLastError());
+}
+
+template <typename T, int D>
+static int launch_fwd_vec(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
+                          const void* loc, const void* attn, void* out, cudaStream_t st) {
+  if (pr.ref) return launch_fwd_vec_impl<T, D, true>(pr, value, shapes, lsi, loc, attn, out, st);
+  return launch_fwd_vec_impl<T, D, false>(pr, value, shapes, lsi, loc, attn, out, st);
 }
 
 template <typename T>
@@ -661,6 +789,7 @@ static int launch_fwd(const Problem& pr, const void* value, const int64_t* shape
       }
     }
   }
+  if (pr.ref) return MSDA_ERR_FUSED_UNSUPPORTED;
   using Aux = typename Traits<T>::Aux;
   const int grid = (pr.total_pairs + kWarps - 1) / kWarps;
   msda_fwd_any_kernel<T><<<grid, kThreads, 0, st>>>(
@@ -670,38 +799,47 @@ static int launch_fwd(const Problem& pr, const void* value, const int64_t* shape
   return static_cast<int>(cudaGetLastError());
 }
 
-template <typename T, int D>
-static int launch_bwd_vec(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
-                          const void* loc, const void* attn, const void* go, float* gv32, __half* gv16,
-                          const uint32_t* ctrl, void* gloc, void* gattn, bool use16, int depth, cudaStream_t st) {
+template <typename T, int D, bool FUSED>
+static int launch_bwd_vec_impl(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
+                               const void* loc, const void* attn, const void* go, float* gv32, __half* gv16,
+                               const uint32_t* ctrl, void* gloc, void* gattn, bool use16, int depth, cudaStream_t st) {
   constexpr int GPW = 32 / (D / (16 / static_cast<int>(sizeof(T))));
-  const size_t smem = vec_smem_bytes<T, D>(pr.L, pr.P);
+  const size_t smem = vec_smem_bytes<T, D>(pr.L, pr.P, FUSED);
   if (smem > 200 * 1024) return MSDA_ERR_BAD_SHAPE;
   const int per_cta = kWarps * GPW;
   const int grid = (pr.total_pairs + per_cta - 1) / per_cta;
   cudaError_t e;
   if constexpr (sizeof(T) == 2) {
     if (use16) {
-      e = allow_smem(msda_bwd_vec_kernel<T, D, true>, smem);
+      e = allow_smem(msda_bwd_vec_kernel<T, D, true, FUSED>, smem);
       if (e != cudaSuccess) return static_cast<int>(e);
       ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD, st);
-      msda_bwd_vec_kernel<T, D, true><<<grid, kThreads, smem, st>>>(
+      msda_bwd_vec_kernel<T, D, true, FUSED><<<grid, kThreads, smem, st>>>(
           static_cast<const T*>(value), shapes, lsi, static_cast<const float*>(loc), static_cast<const float*>(attn),
-          static_cast<const T*>(go), nullptr, gv16, ctrl, static_cast<float*>(gloc),
+          pr.ref, pr.R, static_cast<const T*>(go), nullptr, gv16, ctrl, static_cast<float*>(gloc),
           static_cast<float*>(gattn), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth);
       ++g_last_launches, ++g_total_launches;
       return static_cast<int>(cudaGetLastError());
     }
   }
-  e = allow_smem(msda_bwd_vec_kernel<T, D, false>, smem);
+  e = allow_smem(msda_bwd_vec_kernel<T, D, false, FUSED>, smem);
   if (e != cudaSuccess) return static_cast<int>(e);
   ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD, st);
-  msda_bwd_vec_kernel<T, D, false><<<grid, kThreads, smem, st>>>(
+  msda_bwd_vec_kernel<T, D, false, FUSED><<<grid, kThreads, smem, st>>>(
       static_cast<const T*>(value), shapes, lsi, static_cast<const float*>(loc), static_cast<const float*>(attn),
-      static_cast<const T*>(go), gv32, nullptr, nullptr, static_cast<float*>(gloc), static_cast<float*>(gattn),
+      pr.ref, pr.R, static_cast<const T*>(go), gv32, nullptr, nullptr, static_cast<float*>(gloc), static_cast<float*>(gattn),
       pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth);
   ++g_last_launches, ++g_total_launches;
   return static_cast<int>(cudaGetLastError());
+}
+
+template <typename T, int D>
+static int launch_bwd_vec(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
+                          const void* loc, const void* attn, const void* go, float* gv32, __half* gv16,
+                          const uint32_t* ctrl, void* gloc, void* gattn, bool use16, int depth, cudaStream_t st) {
+  if (pr.ref)
+    return launch_bwd_vec_impl<T, D, true>(pr, value, shapes, lsi, loc, attn, go, gv32, gv16, ctrl, gloc, gattn, use16, depth, st);
+  return launch_bwd_vec_impl<T, D, false>(pr, value, shapes, lsi, loc, attn, go, gv32, gv16, ctrl, gloc, gattn, use16, depth, st);
 }
 
 template <typename T>
@@ -720,7 +858,10 @@ static int launch_bwd(const Problem& pr, const void* value, const int64_t* shape
   if (!k16) {
     e = cudaMemsetAsync(gv, 0, n_value * sizeof(T), st);
   } else if (use16) {
-    e = cudaMemsetAsync(scratch, 0, f16_scratch_bytes(pr.N, pr.S, pr.M, pr.D, pr.Lq, pr.L, pr.P, depth), st);
+    msda_zero_f16_buckets_kernel<<<148 * 8, 256, 0, st>>>(static_cast<uint4*>(scratch), kF16CtrlBytes / 16, shapes, lsi,
+                                                         pr.N, pr.M, pr.D, pr.Lq, pr.L, pr.P, depth);
+    ++g_last_launches, ++g_total_launches;
+    e = cudaGetLastError();
     ctrl = static_cast<uint32_t*>(scratch);
     acc16 = reinterpret_cast<__half*>(static_cast<char*>(scratch) + kF16CtrlBytes);
   } else {
@@ -752,6 +893,7 @@ static int launch_bwd(const Problem& pr, const void* value, const int64_t* shape
     }
   }
   if (!done) {
+    if (pr.ref) return MSDA_ERR_FUSED_UNSUPPORTED;
     using Aux = typename Traits<T>::Aux;
     const int grid = (pr.total_pairs + kWarps - 1) / kWarps;
     if constexpr (k16) {
@@ -800,7 +942,7 @@ static int launch_bwd(const Problem& pr, const void* value, const int64_t* shape
 // =====================================================================================================
 using namespace msda;
 
-extern "C" int msda_abi_version(void) { return 2; }
+extern "C" int msda_abi_version(void) { return 3; }
 
 extern "C" const char* msda_error_string(int code) {
   switch (code) {
@@ -811,6 +953,8 @@ extern "C" const char* msda_error_string(int code) {
     case MSDA_ERR_MISALIGNED: return "buffer is not 16-byte aligned";
     case MSDA_ERR_IM2COL_STEP: return "batch size must be divisible by min(batch, im2col_step)";
     case MSDA_ERR_SCRATCH_TOO_SMALL: return "scratch buffer missing or too small";
+    case MSDA_ERR_FUSED_UNSUPPORTED:
+      return "fused pre-op needs float32/bfloat16/float16 values with head dim 16/32/64/128 and reference points of width 2 or 4";
     default: break;
   }
   if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
@@ -904,6 +1048,88 @@ extern "C" int msda_backward(const void* value, const int64_t* spatial_shapes, c
     case MSDA_F16:
       return launch_bwd<__half>(pr, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
                                 grad_value, grad_sampling_loc, grad_attn_weight, scratch, flags, st);
+  }
+  return MSDA_ERR_BAD_DTYPE;
+}
+
+// ---- fused pre-op entry points ---------------------------------------------------
+extern "C" int msda_fused_supported(int D, int value_dtype) {
+  const bool d_ok = D == 16 || D == 32 || D == 64 || D == 128;
+  return (d_ok && (value_dtype == MSDA_F32 || value_dtype == MSDA_BF16 || value_dtype == MSDA_F16)) ? 1 : 0;
+}
+
+
+static int fused_validate(const Problem& pr, int value_dtype, int ref_dim) {
+  if (ref_dim != 2 && ref_dim != 4) return MSDA_ERR_FUSED_UNSUPPORTED;
+  if (!msda_fused_supported(pr.D, value_dtype)) return MSDA_ERR_FUSED_UNSUPPORTED;
+  if (static_cast<unsigned long long>(pr.S) * pr.M * pr.D * sizeof(float) >= (1ull << 32)) return MSDA_ERR_FUSED_UNSUPPORTED;
+  return MSDA_OK;
+}
+
+extern "C" int msda_fused_forward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                  const void* reference_points, int ref_dim, const void* sampling_offsets,
+                                  const void* attn_logits, void* output,
+                                  int N, int S, int M, int D, int Lq, int L, int P,
+                                  int value_dtype, int im2col_step, void* stream) {
+  g_last_launches = 0;
+  if (!value || !spatial_shapes || !level_start_index || !reference_points || !sampling_offsets || !attn_logits || !output)
+    return MSDA_ERR_NULL_POINTER;
+  Problem pr{N, S, M, D, Lq, L, P, 0};
+  int v = validate(pr, value_dtype, im2col_step);
+  if (v != MSDA_OK) return v;
+  v = fused_validate(pr, value_dtype, ref_dim);
+  if (v != MSDA_OK) return v;
+  pr.total_pairs = N * Lq * M;
+  pr.ref = static_cast<const float*>(reference_points);
+  pr.R = ref_dim;
+  if (!aligned16(value) || !aligned16(sampling_offsets) || !aligned16(attn_logits) || !aligned16(output) ||
+      !aligned16(reference_points))
+    return MSDA_ERR_MISALIGNED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (value_dtype) {
+    case MSDA_F32: return launch_fwd<float>(pr, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, output, st);
+    case MSDA_BF16: return launch_fwd<__nv_bfloat16>(pr, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, output, st);
+    case MSDA_F16: return launch_fwd<__half>(pr, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, output, st);
+  }
+  return MSDA_ERR_BAD_DTYPE;
+}
+
+extern "C" int msda_fused_backward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                   const void* reference_points, int ref_dim, const void* sampling_offsets,
+                                   const void* attn_logits, const void* grad_output,
+                                   void* grad_value, void* grad_sampling_offsets, void* grad_attn_logits,
+                                   void* scratch, size_t scratch_bytes,
+                                   int N, int S, int M, int D, int Lq, int L, int P,
+                                   int value_dtype, int im2col_step, int flags, void* stream) {
+  g_last_launches = 0;
+  if (!value || !spatial_shapes || !level_start_index || !reference_points || !sampling_offsets || !attn_logits ||
+      !grad_output || !grad_value || !grad_sampling_offsets || !grad_attn_logits)
+    return MSDA_ERR_NULL_POINTER;
+  Problem pr{N, S, M, D, Lq, L, P, 0};
+  int v = validate(pr, value_dtype, im2col_step);
+  if (v != MSDA_OK) return v;
+  v = fused_validate(pr, value_dtype, ref_dim);
+  if (v != MSDA_OK) return v;
+  pr.total_pairs = N * Lq * M;
+  pr.ref = static_cast<const float*>(reference_points);
+  pr.R = ref_dim;
+  if (!aligned16(value) || !aligned16(sampling_offsets) || !aligned16(attn_logits) || !aligned16(grad_output) ||
+      !aligned16(grad_value) || !aligned16(grad_sampling_offsets) || !aligned16(grad_attn_logits) ||
+      !aligned16(scratch) || !aligned16(reference_points))
+    return MSDA_ERR_MISALIGNED;
+  const size_t need = msda_backward_scratch_bytes(N, S, M, D, Lq, L, P, value_dtype, flags);
+  if (need > 0 && (!scratch || scratch_bytes < need)) return MSDA_ERR_SCRATCH_TOO_SMALL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (value_dtype) {
+    case MSDA_F32:
+      return launch_bwd<float>(pr, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, grad_output,
+                               grad_value, grad_sampling_offsets, grad_attn_logits, scratch, flags, st);
+    case MSDA_BF16:
+      return launch_bwd<__nv_bfloat16>(pr, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, grad_output,
+                                       grad_value, grad_sampling_offsets, grad_attn_logits, scratch, flags, st);
+    case MSDA_F16:
+      return launch_bwd<__half>(pr, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, grad_output,
+                                grad_value, grad_sampling_offsets, grad_attn_logits, scratch, flags, st);
   }
   return MSDA_ERR_BAD_DTYPE;
 }

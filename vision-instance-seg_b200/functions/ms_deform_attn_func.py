@@ -36,3 +36,34 @@ class MSDeformAttnFunction(Function):
         grad_value, grad_sampling_loc, grad_attn_weight = MSDA.ms_deform_attn_backward(
             value, shapes, level_start, sampling_locations, attention_weights, grad_output, ctx.im2col_step)
         return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
+
+
+class MSDeformAttnFusedFunction(Function):
+    """Opt-in fused variant: consumes what ``MSDeformAttn.forward`` holds *before* it builds
+    ``sampling_locations`` / softmaxed ``attention_weights`` — ``reference_points (N, Lq, L, 2|4)``, the raw
+    ``sampling_offsets (N, Lq, M, L, P, 2)`` and ``attention logits (N, Lq, M, L*P)`` — and returns the same
+    ``(N, Lq, M*D)`` output as ``MSDeformAttnFunction`` would on the derived tensors.  Gradients: value, offsets,
+    logits.  ``reference_points`` must not require grad (the module composes the plain operator in that case)."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, reference_points, sampling_offsets,
+                attention_logits, im2col_step):
+        ctx.im2col_step = im2col_step
+        output = MSDA.ms_deform_attn_fused_forward(value, value_spatial_shapes, value_level_start_index,
+                                                   reference_points, sampling_offsets, attention_logits, im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, reference_points,
+                              sampling_offsets, attention_logits)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, level_start, reference_points, sampling_offsets, attention_logits = ctx.saved_tensors
+        if ctx.needs_input_grad[3]:
+            raise RuntimeError("MSDeformAttnFusedFunction does not differentiate reference_points; "
+                               "use MSDeformAttnFunction on the materialised sampling locations instead")
+        grad_output = grad_output.contiguous()
+        grad_value, grad_off, grad_logits = MSDA.ms_deform_attn_fused_backward(
+            value, shapes, level_start, reference_points, sampling_offsets, attention_logits, grad_output,
+            ctx.im2col_step)
+        return grad_value, None, None, None, grad_off, grad_logits, None

@@ -1,1 +1,1 @@
-from .ms_deform_attn import MSDeformAttn  # noqa: F401
+from .ms_deform_attn import MSDeformAttn, set_fused_preop  # noqa: F401

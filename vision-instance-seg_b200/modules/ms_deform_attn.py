@@ -19,7 +19,8 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
-from ..functions import MSDeformAttnFunction
+from .. import MultiScaleDeformableAttention as MSDA
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
 
 
 def _is_power_of_2(n):
@@ -28,7 +29,23 @@ def _is_power_of_2(n):
     return (n & (n - 1) == 0) and n != 0
 
 
+def set_fused_preop(module: nn.Module, enabled: bool = True) -> int:
+    """Switch the opt-in fused pre-op (softmax + sampling-location arithmetic folded into the kernels, SURVEY.md §8f
+    rank 1) on every ``MSDeformAttn`` below ``module``; returns how many were switched."""
+    n = 0
+    for m in module.modules():
+        if isinstance(m, MSDeformAttn):
+            m.fused_preop = bool(enabled)
+            n += 1
+    return n
+
+
 class MSDeformAttn(nn.Module):
+    #: opt-in: fold softmax(L*P) and ``reference_points (+) sampling_offsets`` into the CUDA kernels instead of
+    #: materialising ``sampling_locations`` / ``attention_weights`` (same maths and rounding order; no new parameters,
+    #: so checkpoints are unaffected).  Constructor signature stays upstream's; flip it with ``set_fused_preop``.
+    fused_preop = False
+
     def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
         """Multi-Scale Deformable Attention Module
         :param d_model      hidden dimension
@@ -101,6 +118,15 @@ class MSDeformAttn(nn.Module):
             .view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
         attention_weights = self.attention_weights(query) \
             .view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
+        if reference_points.shape[-1] not in (2, 4):
+            raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead."
+                             .format(reference_points.shape[-1]))
+        if self.fused_preop and MSDA.fused_supported(value, reference_points) \
+                and not (torch.is_grad_enabled() and reference_points.requires_grad):
+            output = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index,
+                                                     reference_points.contiguous(), sampling_offsets.contiguous(),
+                                                     attention_weights.contiguous(), self.im2col_step)
+            return self.output_proj(output)
         attention_weights = F.softmax(attention_weights, -1) \
             .view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
         if reference_points.shape[-1] == 2:        # encoder: points; offsets are in pixels of each level
