@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    ap.add_argument("--fused-preop", action="store_true",
+                    help="train-step workloads: fold softmax + sampling-location arithmetic into the kernels")
     return ap.parse_args()
 
 
@@ -125,7 +127,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_oracle_step_time(cfg, batch, steps, warmup):
+def cpu_oracle_step_time(cfg, batch, steps, warmup, min_seconds=0.0):
     """Times the CPU oracle (torch restatement of ms_deform_attn_core_pytorch, fp32, all host threads) on one
     layer's forward+backward of `batch` images of the workload.  Returns (seconds per step, points per step)."""
     import torch
@@ -144,7 +146,7 @@ def cpu_oracle_step_time(cfg, batch, steps, warmup):
     for _ in range(warmup):
         step()
     times = []
-    for _ in range(steps):
+    while len(times) < steps or sum(times) < min_seconds:
         t0 = time.perf_counter()
         step()
         times.append(time.perf_counter() - t0)
@@ -324,11 +326,12 @@ def run_b200(args):
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        times, pts = cpu_oracle_step_time(cfg, args.cpu_sample_batch, 3, 1)
+        times, pts = cpu_oracle_step_time(cfg, args.cpu_sample_batch, 3, 1, min_seconds=12.0)
         cores = os.cpu_count() or 1
         cpu_baseline = {"value": pts * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{args.workload}: {args.cpu_sample_batch} image(s) x 1 layer fwd+bwd, fp32, 3 timed runs "
-                                  f"after 1 warm-up ({sum(times):.1f} s), oracle ms_deform_attn_core_pytorch restatement"}
+                        "sample": f"{args.workload}: {args.cpu_sample_batch} image(s) x 1 layer fwd+bwd per run, fp32, "
+                                  f"{len(times)} timed runs after 1 warm-up ({sum(times):.1f} s of CPU work), oracle "
+                                  f"ms_deform_attn_core_pytorch restatement on torch CPU with {cores} threads"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -340,6 +343,138 @@ def run_b200(args):
                    "grad_allreduce_bytes": D.ENCODER_GRAD_ELEMENTS * 4 if world > 1 else 0,
                    "l2_policy": f"{layers} independent input sets ({layers * (ab['fwd'] + ab['bwd']) / 1e9:.1f} GB touched per step) >> 126 MB L2; no flush needed"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# training-step workloads (BASELINE.json configs[4]): 6-layer encoder, batch-sharded, gradient all-reduce, AdamW
+# ------------------------------------------------------------------------------------------------------
+def run_train_step(args):
+    import torch
+    import vision_instance_seg_b200 as pkg
+    from vision_instance_seg_b200 import _lib, distributed as D, workloads as W
+    from vision_instance_seg_b200.modules.encoder import MSDeformAttnTransformerEncoderOnly
+
+    rank, local_rank, world = D.init_process_group()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = pkg.load_library()
+    cfg = W.CONFIGS[args.workload]
+    global_batch = args.batch or cfg["batch"]
+    start, count = D.shard_batch(global_batch, world, rank)
+    if count == 0:
+        raise SystemExit("global batch smaller than the number of ranks")
+    layers = args.layers or cfg["layers"]
+    shapes, M, P, C = cfg["shapes"], cfg["heads"], cfg["points"], cfg["d_model"]
+    L = len(shapes)
+    S = sum(h * w for h, w in shapes)
+
+    torch.manual_seed(1234)                     # identical parameters on every rank
+    enc = MSDeformAttnTransformerEncoderOnly(d_model=C, nhead=M, num_encoder_layers=layers, dim_feedforward=cfg["d_ffn"],
+                                             dropout=0.0, num_feature_levels=L, enc_n_points=P).to(dev)
+    with torch.no_grad():                       # trained-like projections: offsets / weights depend on the query
+        for layer in enc.encoder.layers:
+            layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
+            layer.self_attn.attention_weights.weight.normal_(0, 0.05)
+    pkg.set_fused_preop(enc, args.fused_preop)
+    buckets = D.GradientBuckets(D.encoder_gradient_groups(enc), device=dev)
+    opt = torch.optim.AdamW(enc.parameters(), lr=1e-5, fused=True)
+    host_srcs, host_pos = W.make_feature_pyramid(shapes, count, C, seed=99 + start, device="cpu", pin=True)
+    srcs = [t.to(dev) for t in host_srcs]
+    pos = [t.to(dev) for t in host_pos]
+    pts_per_step = global_batch * S * M * L * P * layers
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(from_host=False):
+        x = [t.to(dev, non_blocking=True) for t in host_srcs] if from_host else srcs
+        buckets.zero()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            memory, _, _ = enc(x, None, pos)
+        loss = memory.float().square().mean()
+        loss.backward()
+        buckets.wait()
+        opt.step()
+        if from_host:
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    lib.msda_profile_enable(1)
+    launches0 = lib.msda_total_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    t1 = time.time()
+    lib.msda_profile_enable(0)
+    launches = lib.msda_total_launch_count() - launches0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms_per_step = D.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+    records = _lib.profile_collect()
+    fwd_ms = [t for t, k in records if k == 1]
+    bwd_ms = [t for t, k in records if k == 2]
+    final_loss = float(loss)
+
+    e2e = None
+    if not args.no_e2e:
+        step(True)
+        barrier()
+        e0.record()
+        for _ in range(args.e2e_steps):
+            step(True)
+        e1.record()
+        barrier()
+        e2e_ms = D.max_over_ranks(e0.elapsed_time(e1), dev) / args.e2e_steps
+        e2e = {"value": pts_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": args.e2e_steps,
+               "h2d_bytes_per_step": sum(t.numel() * 4 for t in host_srcs), "d2h_bytes_per_step": 4,
+               "api": "MSDeformAttnTransformerEncoderOnly.forward/backward + GradientBuckets + AdamW; feature pyramid copied "
+                      "from pinned host memory every step, loss copied back"}
+    if rank != 0:
+        return 0
+    peak, peak_src = measured_peak_gbs()
+    ab = W.algorithmic_bytes(count, S, S, M, C // M, L, P, 2)
+    if args.fused_preop:        # sampling locations / attention weights never reach HBM: raw offsets + logits instead (same sizes)
+        pass
+    roofline = None
+    if bwd_ms:
+        bwd_avg, fwd_avg = statistics.mean(bwd_ms), statistics.mean(fwd_ms)
+        roofline = {"bound": "hbm", "kernel": "msda_bwd (backward gather + grad_value scatter)",
+                    "achieved": ab["bwd"] / (bwd_avg * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": ab["bwd"] / (bwd_avg * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": ab["bwd"], "avg_launch_ms": bwd_avg, "launches_timed": len(bwd_ms),
+                    "forward": {"avg_launch_ms": fwd_avg, "algorithmic_bytes_per_launch": ab["fwd"],
+                                "frac": ab["fwd"] / (fwd_avg * 1e-3) / 1e9 / peak},
+                    "msda_share_of_step": (sum(bwd_ms) + sum(fwd_ms)) / args.steps / ms_per_step}
+    line = {
+        "metric": METRIC, "value": pts_per_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": args.workload, "global_batch": global_batch, "per_gpu_batch": count, "layers": layers,
+                   "levels": shapes, "queries": S, "heads": M, "head_dim": C // M, "points": P, "d_ffn": cfg["d_ffn"],
+                   "fused_preop": bool(args.fused_preop), "optimizer": "AdamW(fused)", "autocast": "bf16",
+                   "parallelism": f"dp{world}", "grad_allreduce_bytes": int(buckets.flat.numel() * 4) if world > 1 else 0,
+                   "grad_buckets": len(buckets.slices), "points_per_step": pts_per_step, "final_loss": final_loss,
+                   "l2_policy": "activations of one step (GBs) >> 126 MB L2; no flush needed"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -358,6 +493,9 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    from vision_instance_seg_b200 import workloads as W
+    if W.CONFIGS[args.workload]["kind"] == "train_step":
+        return run_train_step(args)
     return run_b200(args)
 
 

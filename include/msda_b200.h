@@ -141,8 +141,12 @@ int msda_profile_collect(float* ms, int* kinds, int max_records);
  * sampled point at the encoder shape).
  *
  *   reference_points   (N, Lq, L, ref_dim)   float32
- *   sampling_offsets   (N, Lq, M, L, P, 2)   float32   raw output of the sampling_offsets Linear
- *   attn_logits        (N, Lq, M, L*P)       float32   raw output of the attention_weights Linear
+ *   sampling_offsets   (N, Lq, M, L, P, 2)   aux dtype   raw output of the sampling_offsets Linear
+ *   attn_logits        (N, Lq, M, L*P)       aux dtype   raw output of the attention_weights Linear
+ *
+ * aux_dtype is MSDA_F32, or — for 16-bit values — the value dtype itself: inside a torch.autocast region the two
+ * Linears hand over bfloat16 / float16, which the kernels then read (and whose gradients they write) directly instead
+ * of through fp32 copies; all arithmetic stays fp32.
  *
  * The backward returns the gradients of sampling_offsets and attn_logits (softmax and offset chain rules applied
  * in shared memory); reference_points receives no gradient here (callers that need one compose the plain operator).
@@ -155,7 +159,7 @@ int msda_fused_forward(const void* value, const int64_t* spatial_shapes, const i
                        const void* reference_points, int ref_dim, const void* sampling_offsets,
                        const void* attn_logits, void* output,
                        int N, int S, int M, int D, int Lq, int L, int P,
-                       int value_dtype, int im2col_step, void* stream);
+                       int value_dtype, int aux_dtype, int im2col_step, void* stream);
 
 int msda_fused_backward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
                         const void* reference_points, int ref_dim, const void* sampling_offsets,
@@ -163,7 +167,7 @@ int msda_fused_backward(const void* value, const int64_t* spatial_shapes, const 
                         void* grad_value, void* grad_sampling_offsets, void* grad_attn_logits,
                         void* scratch, size_t scratch_bytes,
                         int N, int S, int M, int D, int Lq, int L, int P,
-                        int value_dtype, int im2col_step, int flags, void* stream);
+                        int value_dtype, int aux_dtype, int im2col_step, int flags, void* stream);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,26 @@ def _worker(rank, world, port, q):
     bucket.flat.fill_(float(rank + 1))
     bucket.allreduce_async()
     bucket.wait()
-    q.put((rank, start, count, t_max, t_sum, float(bucket.flat[0]), float(bucket.flat[-1])))
+    # per-layer buckets reduced from backward hooks: grads must come out as the mean over the ranks
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.Tanh(), torch.nn.Linear(8, 3))
+    buckets = D.GradientBuckets([list(net[2].parameters()), list(net[0].parameters())], device="cpu")
+    x = torch.full((2, 4), float(rank + 1))
+    net(x).square().sum().backward()
+    buckets.wait()
+    local = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.Tanh(), torch.nn.Linear(8, 3))
+    local.load_state_dict(net.state_dict())
+    want = None
+    for rk in range(world):
+        local.zero_grad()
+        local(torch.full((2, 4), float(rk + 1))).square().sum().backward()
+        gs = torch.cat([p.grad.flatten() for p in list(local[2].parameters()) + list(local[0].parameters())])
+        want = gs / world if want is None else want + gs / world
+    ok_buckets = bool(torch.allclose(buckets.flat, want, rtol=1e-5, atol=1e-6)) and buckets.launched == 2 \
+        and net[0].weight.grad.data_ptr() == buckets.flat[buckets.slices[1][0]:].data_ptr()
+    buckets.zero()
+    ok_buckets = ok_buckets and float(net[0].weight.grad.abs().max()) == 0.0
+    q.put((rank, start, count, t_max, t_sum, float(bucket.flat[0]), float(bucket.flat[-1]), ok_buckets))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -51,6 +70,7 @@ def test_world_size_2_gloo():
     assert all(r[3] == 11.0 for r in res)                            # max over ranks
     assert all(r[4] == 5.0 for r in res)                             # all images accounted for
     assert all(r[5] == 1.5 and r[6] == 1.5 for r in res)             # mean of (1, 2)
+    assert all(r[7] for r in res)                                    # hook-driven per-layer buckets
 
 
 def test_shard_batch_covers_everything():

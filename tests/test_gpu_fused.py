@@ -67,6 +67,30 @@ def test_fused_matches_oracle_encoder_like(ops, ref_dim, dtype):
     check_fused(ops, fused_problem(2, 8, 32, 77, [(16, 12), (8, 6), (4, 3)], 4, ref_dim, seed=ref_dim), dtype)
 
 
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("LP", [(3, 4), (2, 3)])
+def test_fused_16bit_offsets_and_logits(ops, ref_dim, dtype, LP):
+    """Inside torch.autocast the Linears emit 16-bit offsets / logits; the kernels read them (and write their gradients)
+    directly.  The oracle sees the same 16-bit-rounded operands; gradients are compared after one 16-bit rounding."""
+    L, P = LP                       # (2, 3): L*P % 4 != 0 -> scalar staging path
+    shapes = [(16, 12), (8, 6), (4, 3)][:L]
+    value, ss, lsi, ref, off, logits, go = fused_problem(2, 8, 32, 45, shapes, P, ref_dim, seed=9 + ref_dim)
+    dev = torch.device("cuda:0")
+    v = value.to(dev, dtype).requires_grad_(True)
+    o = off.to(dev, dtype).requires_grad_(True)
+    lg = logits.to(dev, dtype).requires_grad_(True)
+    out = ops.MSDeformAttnFusedFunction.apply(v, ss.to(dev), lsi.to(dev), ref.to(dev), o, lg, 64)
+    out.backward(go.to(dev, dtype))
+    torch.cuda.synchronize()
+    assert o.grad.dtype == dtype and lg.grad.dtype == dtype and out.dtype == dtype
+    want = ms_deform_attn_fused_oracle_grads(value.to(dtype).double(), ss, ref.double(), off.to(dtype).double(),
+                                             logits.to(dtype).double(), go.to(dtype).double())
+    tol = {torch.bfloat16: 2e-2, torch.float16: 5e-3}[dtype]
+    for name, g, w in zip(("out", "grad_value", "grad_offsets", "grad_logits"), (out, v.grad, o.grad, lg.grad), want):
+        assert rel_to_max(g, w) < tol, f"{name} ({dtype}, ref_dim {ref_dim})"
+
+
 @pytest.mark.parametrize("D", [16, 32, 64, 128])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_fused_all_vector_head_dims(ops, D, dtype):

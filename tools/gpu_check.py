@@ -47,7 +47,37 @@ def timing(name, maker, dtype, flags=0, **kw):
                           fwd_GBps=ab["fwd"] / t_f / 1e6, bwd_GBps=ab["bwd"] / t_b / 1e6,
                           fwdbwd_Gpts=ab["points"] / (t_f + t_b) / 1e6)), flush=True)
 
+def timing_fused(name, dtype, shapes, batch, ref_dim=2, queries=None):
+    from vision_instance_seg_b200 import MSDeformAttnFusedFunction
+    ss = W.make_spatial_shapes(shapes, dev); lsi = W.make_level_start_index(ss)
+    S = int(ss.prod(1).sum()); L = len(shapes); M, D, P = 8, 32, 4
+    Lq = S if queries is None else queries
+    g = torch.Generator(device=dev).manual_seed(7)
+    v = torch.randn(batch, S, M, D, generator=g, device=dev).to(dtype)
+    if ref_dim == 2:
+        ref = W.get_reference_points(ss, torch.ones(batch, L, 2, device=dev), dev).contiguous()
+    else:
+        ref = torch.cat([torch.rand(batch, Lq, 1, 2, generator=g, device=dev).expand(-1, -1, L, -1),
+                         torch.rand(batch, Lq, 1, 2, generator=g, device=dev).expand(-1, -1, L, -1) * 0.45 + 0.05], -1).contiguous()
+    off = torch.randn(batch, Lq, M, L, P, 2, generator=g, device=dev) * 2.0
+    lg = torch.randn(batch, Lq, M, L * P, generator=g, device=dev)
+    go = torch.randn(batch, Lq, M * D, device=dev, dtype=dtype)
+    t_f = timeit(lambda: MSDA.ms_deform_attn_fused_forward(v, ss, lsi, ref, off, lg, 128))
+    t_b = timeit(lambda: MSDA.ms_deform_attn_fused_backward(v, ss, lsi, ref, off, lg, go, 128))
+    pts = batch * Lq * M * L * P
+    print(json.dumps(dict(case=name, dtype=str(dtype), fused=True, fwd_ms=t_f, bwd_ms=t_b, points=pts,
+                          fwdbwd_Gpts=pts / (t_f + t_b) / 1e6)), flush=True)
+
+
 if __name__ == "__main__":
+    if "--fused-only" in sys.argv:
+        c3 = W.CONFIGS["cfg3_swinl_1024_bf16"]["shapes"]
+        timing("cfg3", W.make_encoder_inputs, torch.bfloat16, shapes=c3, batch=16)
+        timing_fused("cfg3_fused", torch.bfloat16, c3, 16)
+        timing_fused("cfg3_fused_fp32", torch.float32, c3, 16)
+        timing("cfg4_dec", W.make_decoder_inputs, torch.bfloat16, shapes=c3, batch=16)
+        timing_fused("cfg4_dec_fused", torch.bfloat16, c3, 16, ref_dim=4, queries=300)
+        sys.exit(0)
     small = [(16, 16), (8, 8), (4, 4)]
     c1 = W.CONFIGS["cfg1_512_fp32"]["shapes"]; c3 = W.CONFIGS["cfg3_swinl_1024_bf16"]["shapes"]
     parity("small_enc", W.make_encoder_inputs, torch.float32, shapes=small, batch=2)

@@ -129,6 +129,17 @@ def fused_supported(value: torch.Tensor, reference_points: torch.Tensor) -> bool
     return bool(_lib.load_library().msda_fused_supported(int(value.shape[-1]), _DTYPES[value.dtype]))
 
 
+def _fused_aux(value, sampling_offsets, attn_logits):
+    """Offsets / logits are consumed as they are when both are float32, or both already in the 16-bit value dtype (what the
+    Linears emit inside torch.autocast); any other combination is brought to float32."""
+    if value.dtype in (torch.bfloat16, torch.float16) and sampling_offsets.dtype == value.dtype \
+            and attn_logits.dtype == value.dtype:
+        return sampling_offsets, attn_logits, value.dtype
+    off = sampling_offsets if sampling_offsets.dtype == torch.float32 else sampling_offsets.float()
+    logits = attn_logits if attn_logits.dtype == torch.float32 else attn_logits.float()
+    return off, logits, torch.float32
+
+
 def _fused_dims(value, spatial_shapes, reference_points, sampling_offsets, attn_logits):
     if value.dim() != 4 or sampling_offsets.dim() != 6 or reference_points.dim() != 4:
         raise RuntimeError("value must be (N, S, M, D), sampling_offsets (N, Lq, M, L, P, 2), reference_points (N, Lq, L, 2|4)")
@@ -150,8 +161,7 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, refer
         raise RuntimeError(f"ms_deform_attn_fused_forward not implemented for '{value.dtype}'")
     N, S, M, D, Lq, L, P, R = _fused_dims(value, spatial_shapes, reference_points, sampling_offsets, attn_logits)
     ref = reference_points if reference_points.dtype == torch.float32 else reference_points.float()
-    off = sampling_offsets if sampling_offsets.dtype == torch.float32 else sampling_offsets.float()
-    logits = attn_logits if attn_logits.dtype == torch.float32 else attn_logits.float()
+    off, logits, aux = _fused_aux(value, sampling_offsets, attn_logits)
     shapes = _meta(spatial_shapes, value.device)
     lsi = _meta(level_start_index, value.device)
     lib = _lib.load_library()
@@ -162,7 +172,7 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, refer
         stream = torch.cuda.current_stream().cuda_stream
         rc = lib.msda_fused_forward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), ref.data_ptr(), R, off.data_ptr(),
                                     logits.data_ptr(), out.data_ptr(), N, S, M, D, Lq, L, P, _DTYPES[value.dtype],
-                                    int(im2col_step), stream)
+                                    _DTYPES[aux], int(im2col_step), stream)
     _lib.check(rc, "ms_deform_attn_fused_forward")
     return out
 
@@ -178,8 +188,7 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, refe
         raise RuntimeError(f"ms_deform_attn_fused_backward not implemented for '{value.dtype}'")
     N, S, M, D, Lq, L, P, R = _fused_dims(value, spatial_shapes, reference_points, sampling_offsets, attn_logits)
     ref = reference_points if reference_points.dtype == torch.float32 else reference_points.float()
-    off = sampling_offsets if sampling_offsets.dtype == torch.float32 else sampling_offsets.float()
-    logits = attn_logits if attn_logits.dtype == torch.float32 else attn_logits.float()
+    off, logits, aux = _fused_aux(value, sampling_offsets, attn_logits)
     go = grad_output if grad_output.dtype == value.dtype else grad_output.to(value.dtype)
     shapes = _meta(spatial_shapes, value.device)
     lsi = _meta(level_start_index, value.device)
@@ -187,8 +196,8 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, refe
     code = _DTYPES[value.dtype]
     with torch.cuda.device(value.device):
         grad_value = torch.empty_like(value)
-        grad_off = torch.empty(sampling_offsets.shape, dtype=torch.float32, device=value.device)
-        grad_logits = torch.empty(attn_logits.shape, dtype=torch.float32, device=value.device)
+        grad_off = torch.empty(sampling_offsets.shape, dtype=aux, device=value.device)
+        grad_logits = torch.empty(attn_logits.shape, dtype=aux, device=value.device)
         if grad_off.numel() == 0 or value.numel() == 0:
             return [grad_value.zero_(), grad_off.zero_(), grad_logits.zero_()]
         nbytes = lib.msda_backward_scratch_bytes(N, S, M, D, Lq, L, P, code, backward_flags)
@@ -197,7 +206,7 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, refe
         rc = lib.msda_fused_backward(value.data_ptr(), shapes.data_ptr(), lsi.data_ptr(), ref.data_ptr(), R, off.data_ptr(),
                                      logits.data_ptr(), go.data_ptr(), grad_value.data_ptr(), grad_off.data_ptr(),
                                      grad_logits.data_ptr(), scratch.data_ptr() if scratch is not None else None, nbytes,
-                                     N, S, M, D, Lq, L, P, code, int(im2col_step), backward_flags, stream)
+                                     N, S, M, D, Lq, L, P, code, _DTYPES[aux], int(im2col_step), backward_flags, stream)
     _lib.check(rc, "ms_deform_attn_fused_backward")
     if grad_off.dtype != sampling_offsets.dtype:
         grad_off = grad_off.to(sampling_offsets.dtype)

@@ -63,10 +63,10 @@ def _declare(lib):
     lib.msda_fused_supported.restype = i
     lib.msda_fused_supported.argtypes = [i, i]
     lib.msda_fused_forward.restype = i
-    lib.msda_fused_forward.argtypes = [vp, i64p, i64p, vp, i, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]
+    lib.msda_fused_forward.argtypes = [vp, i64p, i64p, vp, i, vp, vp, vp, i, i, i, i, i, i, i, i, i, i, vp]
     lib.msda_fused_backward.restype = i
     lib.msda_fused_backward.argtypes = [vp, i64p, i64p, vp, i, vp, vp, vp, vp, vp, vp, vp, sz,
-                                        i, i, i, i, i, i, i, i, i, i, vp]
+                                        i, i, i, i, i, i, i, i, i, i, i, vp]
     lib.msda_total_launch_count.restype = ctypes.c_longlong
     lib.msda_total_launch_count.argtypes = []
     lib.msda_profile_enable.restype = i

@@ -44,51 +44,83 @@ struct WarpStage {
   int loc_stride, attn_stride;
 };
 
-__device__ __forceinline__ void stage_in(const WarpStage& ws, const float* __restrict__ gl, const float* __restrict__ ga,
+// Rows are moved in quads of 4 elements; AT is float, or the 16-bit value type when the fused kernels consume the
+// Linear outputs of an autocast region directly (8-byte loads / stores, converted to / from the fp32 staging rows).
+template <typename AT> __device__ __forceinline__ float4 load_quad(const AT* __restrict__ base, int i);
+template <> __device__ __forceinline__ float4 load_quad<float>(const float* __restrict__ base, int i) {
+  return __ldg(reinterpret_cast<const float4*>(base) + i);
+}
+template <> __device__ __forceinline__ float4 load_quad<__nv_bfloat16>(const __nv_bfloat16* __restrict__ base, int i) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(base) + i);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                     __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float4 load_quad<__half>(const __half* __restrict__ base, int i) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(base) + i);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename AT> __device__ __forceinline__ void store_quad(AT* __restrict__ base, int i, const float4& v);
+template <> __device__ __forceinline__ void store_quad<float>(float* __restrict__ base, int i, const float4& v) {
+  __stcs(reinterpret_cast<float4*>(base) + i, v);
+}
+template <> __device__ __forceinline__ void store_quad<__nv_bfloat16>(__nv_bfloat16* __restrict__ base, int i, const float4& v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  __stcs(reinterpret_cast<uint2*>(base) + i, make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b)));
+}
+template <> __device__ __forceinline__ void store_quad<__half>(__half* __restrict__ base, int i, const float4& v) {
+  const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  __stcs(reinterpret_cast<uint2*>(base) + i, make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b)));
+}
+
+template <typename AT>
+__device__ __forceinline__ void stage_in(const WarpStage& ws, const AT* __restrict__ gl, const AT* __restrict__ ga,
                                          int nvalid, int LP, int lane) {
   if ((LP & 3) == 0) {
-    const int lv = LP / 2, av = LP / 4;     // float4s per pair row
+    const int lv = LP / 2, av = LP / 4;     // quads per pair row
     for (int i = lane; i < nvalid * lv; i += 32) {
       const int r = i / lv, k = i - r * lv;
-      *reinterpret_cast<float4*>(ws.loc + r * ws.loc_stride + 4 * k) = __ldg(reinterpret_cast<const float4*>(gl) + i);
+      *reinterpret_cast<float4*>(ws.loc + r * ws.loc_stride + 4 * k) = load_quad<AT>(gl, i);
     }
     for (int i = lane; i < nvalid * av; i += 32) {
       const int r = i / av, k = i - r * av;
-      *reinterpret_cast<float4*>(ws.attn + r * ws.attn_stride + 4 * k) = __ldg(reinterpret_cast<const float4*>(ga) + i);
+      *reinterpret_cast<float4*>(ws.attn + r * ws.attn_stride + 4 * k) = load_quad<AT>(ga, i);
     }
   } else {
     for (int i = lane; i < nvalid * 2 * LP; i += 32) {
       const int r = i / (2 * LP), k = i - r * 2 * LP;
-      ws.loc[r * ws.loc_stride + k] = __ldg(gl + i);
+      ws.loc[r * ws.loc_stride + k] = to_acc<AT>(gl[i]);
     }
     for (int i = lane; i < nvalid * LP; i += 32) {
       const int r = i / LP, k = i - r * LP;
-      ws.attn[r * ws.attn_stride + k] = __ldg(ga + i);
+      ws.attn[r * ws.attn_stride + k] = to_acc<AT>(ga[i]);
     }
   }
 }
 
+template <typename AT>
 __device__ __forceinline__ void stage_out(const WarpStage& ws, const float* __restrict__ attn_src,
-                                          float* __restrict__ gl, float* __restrict__ ga,
+                                          AT* __restrict__ gl, AT* __restrict__ ga,
                                           int nvalid, int LP, int lane) {
   if ((LP & 3) == 0) {
     const int lv = LP / 2, av = LP / 4;
     for (int i = lane; i < nvalid * lv; i += 32) {
       const int r = i / lv, k = i - r * lv;
-      __stcs(reinterpret_cast<float4*>(gl) + i, *reinterpret_cast<const float4*>(ws.loc + r * ws.loc_stride + 4 * k));
+      store_quad<AT>(gl, i, *reinterpret_cast<const float4*>(ws.loc + r * ws.loc_stride + 4 * k));
     }
     for (int i = lane; i < nvalid * av; i += 32) {
       const int r = i / av, k = i - r * av;
-      __stcs(reinterpret_cast<float4*>(ga) + i, *reinterpret_cast<const float4*>(attn_src + r * ws.attn_stride + 4 * k));
+      store_quad<AT>(ga, i, *reinterpret_cast<const float4*>(attn_src + r * ws.attn_stride + 4 * k));
     }
   } else {
     for (int i = lane; i < nvalid * 2 * LP; i += 32) {
       const int r = i / (2 * LP), k = i - r * 2 * LP;
-      gl[i] = ws.loc[r * ws.loc_stride + k];
+      gl[i] = from_acc<AT>(ws.loc[r * ws.loc_stride + k]);
     }
     for (int i = lane; i < nvalid * LP; i += 32) {
       const int r = i / LP, k = i - r * LP;
-      ga[i] = attn_src[r * ws.attn_stride + k];
+      ga[i] = from_acc<AT>(attn_src[r * ws.attn_stride + k]);
     }
   }
 }
@@ -98,76 +130,102 @@ __device__ __forceinline__ void stage_out(const WarpStage& ws, const float* __re
 // *before* it materialises sampling_locations / softmaxed attention_weights: the raw outputs of the
 // sampling_offsets and attention_weights Linears plus reference_points (N, Lq, L, R), R = 2 (encoder: points)
 // or 4 (decoder: boxes).  After the warp's rows are staged, each lane group rewrites its own row in place,
-// with the module's arithmetic and rounding order:
-//     R == 2:  loc = ref + off / (W_l, H_l)                       (fp32 division, then add)
+// with the module's arithmetic (see stage_ref for the rounding):
+//     R == 2:  loc = ref + off / (W_l, H_l)
 //     R == 4:  loc = ref_xy + ((off / P) * ref_wh) * 0.5
-//     attn = softmax over the L*P logits of the pair = exp(x - max) / sum
+//     attn = softmax over the L*P logits of the pair = exp(x - max) / sum     (ex2.approx-based exp, one reciprocal)
 // The backward applies the matching chain rules to grad_loc / grad_attn before they leave shared memory:
 //     R == 2:  grad_off = grad_loc / (W_l, H_l);   R == 4:  grad_off = ((grad_loc * 0.5) * ref_wh) / P
 //     grad_logit = (grad_attn - sum_j(grad_attn_j * attn_j)) * attn
 // so sampling_locations / attention_weights and their gradients never exist in HBM.
 // =====================================================================================================
-template <int G>
-__device__ __forceinline__ unsigned group_mask(int g) {
-  if constexpr (G >= 32) return 0xffffffffu;
-  else return ((1u << G) - 1u) << (g * G);
-}
-
-template <int G>
-__device__ __forceinline__ void fused_prepare(float* myloc, float* myattn, const LevelMeta& meta,
-                                              const float* __restrict__ refq, int R, int L, int P, int c, unsigned gmask) {
-  const int LP = L * P;
-  const float Pf = static_cast<float>(P);
-  for (int i = c; i < LP; i += G) {
-    const int l = i / P;
-    const float2 off = *reinterpret_cast<const float2*>(myloc + 2 * i);
-    float x, y;
+// Per (pair, level) affine map of the raw offsets: loc = (rx, ry) + off * (sx, sy), staged as float4 (rx, ry, sx, sy).
+//   R == 2: (sx, sy) = (1 / W_l, 1 / H_l);   R == 4: (sx, sy) = ref_wh * (0.5 / P).
+// For power-of-two W_l, H_l and P (every BASELINE config) this is bit-identical to the module's
+// `ref + off / (W, H)` / `ref_xy + off / P * ref_wh * 0.5`; otherwise it differs by at most one ulp of the offset term.
+// The loads are issued together with the staging loads of the warp's rows, so their latency overlaps.
+__device__ __forceinline__ void stage_ref(float4* __restrict__ sref, const LevelMeta& meta, const float* __restrict__ ref,
+                                          int R, int pair0, int nvalid, int M, int L, int P, int lane) {
+  const float half_over_p = 0.5f / static_cast<float>(P);
+  for (int i = lane; i < nvalid * L; i += 32) {
+    const int r = i / L, l = i - r * L;
+    const float* row = ref + (static_cast<size_t>((pair0 + r) / M) * L + l) * R;
+    float4 v;
     if (R == 2) {
-      const float2 r = __ldg(reinterpret_cast<const float2*>(refq) + l);
-      x = __fadd_rn(r.x, __fdiv_rn(off.x, static_cast<float>(meta.W[l])));
-      y = __fadd_rn(r.y, __fdiv_rn(off.y, static_cast<float>(meta.H[l])));
+      const float2 t = __ldg(reinterpret_cast<const float2*>(row));
+      v = make_float4(t.x, t.y, 1.0f / static_cast<float>(meta.W[l]), 1.0f / static_cast<float>(meta.H[l]));
     } else {
-      const float4 r = __ldg(reinterpret_cast<const float4*>(refq) + l);
-      x = __fadd_rn(r.x, __fmul_rn(__fmul_rn(__fdiv_rn(off.x, Pf), r.z), 0.5f));
-      y = __fadd_rn(r.y, __fmul_rn(__fmul_rn(__fdiv_rn(off.y, Pf), r.w), 0.5f));
+      const float4 t = __ldg(reinterpret_cast<const float4*>(row));
+      v = make_float4(t.x, t.y, __fmul_rn(t.z, half_over_p), __fmul_rn(t.w, half_over_p));
     }
-    *reinterpret_cast<float2*>(myloc + 2 * i) = make_float2(x, y);
+    sref[r * L + l] = v;
   }
-  float mx = -INFINITY;
-  for (int i = c; i < LP; i += G) mx = fmaxf(mx, myattn[i]);
-#pragma unroll
-  for (int s = G / 2; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(gmask, mx, s));
-  float sum = 0.f;
-  for (int i = c; i < LP; i += G) {
-    const float e = expf(__fsub_rn(myattn[i], mx));
-    myattn[i] = e;
-    sum += e;
-  }
-#pragma unroll
-  for (int s = G / 2; s >= 1; s >>= 1) sum += __shfl_xor_sync(gmask, sum, s);
-  for (int i = c; i < LP; i += G) myattn[i] = __fdiv_rn(myattn[i], sum);
-  __syncwarp(gmask);
 }
 
-// grad_loc of point i (level l) -> grad of the raw sampling offset
-__device__ __forceinline__ float2 fused_offset_grad(float gx, float gy, const LevelMeta& meta, const float* __restrict__ refq,
-                                                    int R, int l, int P) {
-  if (R == 2)
-    return make_float2(__fdiv_rn(gx, static_cast<float>(meta.W[l])), __fdiv_rn(gy, static_cast<float>(meta.H[l])));
-  const float4 r = __ldg(reinterpret_cast<const float4*>(refq) + l);
-  const float Pf = static_cast<float>(P);
-  return make_float2(__fdiv_rn(__fmul_rn(__fmul_rn(gx, 0.5f), r.z), Pf), __fdiv_rn(__fmul_rn(__fmul_rn(gy, 0.5f), r.w), Pf));
+// level of point i (i / P) without an integer division: exact for i, P < 2^20
+__device__ __forceinline__ int level_of(int i, float inv_p) {
+  return __float2int_rz(__fmul_rn(static_cast<float>(i) + 0.5f, inv_p));
+}
+
+// Executed by ALL lanes of the warp with full-mask shuffles (per-group masks would leave the warp split into
+// independently scheduled groups for the main loop); padding groups of a ragged last warp shadow row 0 and do not write.
+template <int G>
+__device__ __forceinline__ void fused_prepare(float* myloc, float* myattn, const float4* __restrict__ myref,
+                                              int L, int P, int c, bool active) {
+  const int LP = L * P;
+  const float inv_p = 1.0f / static_cast<float>(P);
+  for (int i = c; i < LP; i += G) {
+    const float4 rs = myref[level_of(i, inv_p)];
+    const float2 off = *reinterpret_cast<const float2*>(myloc + 2 * i);
+    if (active)
+      *reinterpret_cast<float2*>(myloc + 2 * i) =
+          make_float2(__fadd_rn(rs.x, __fmul_rn(off.x, rs.z)), __fadd_rn(rs.y, __fmul_rn(off.y, rs.w)));
+  }
+  // softmax: the first 4 logits of the lane (all of them when L*P <= 4*G, e.g. 16 points on 4 lanes) stay in
+  // registers between the passes; longer rows spill over to shared memory (the shared-memory pipe is what bounds
+  // the gather loop that follows, so every LDS/STS saved here is time saved there)
+  float lg[4];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = c + k * G;
+    lg[k] = i < LP ? myattn[i] : -INFINITY;
+    mx = fmaxf(mx, lg[k]);
+  }
+  for (int i = c + 4 * G; i < LP; i += G) mx = fmaxf(mx, myattn[i]);
+#pragma unroll
+  for (int s = G / 2; s >= 1; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    lg[k] = __expf(lg[k] - mx);           // exp(-inf) = 0 for the padding slots
+    sum += lg[k];
+  }
+  for (int i = c + 4 * G; i < LP; i += G) sum += __expf(myattn[i] - mx);
+#pragma unroll
+  for (int s = G / 2; s >= 1; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+  const float inv = 1.0f / sum;
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = c + k * G;
+      if (i < LP) myattn[i] = lg[k] * inv;
+    }
+    for (int i = c + 4 * G; i < LP; i += G) myattn[i] = __expf(myattn[i] - mx) * inv;
+  }
+  __syncwarp();
 }
 
 // =====================================================================================================
 // Forward, vector path
 // =====================================================================================================
 // FUSED: `loc` / `attn` hold raw sampling offsets / attention logits and `ref` (N, Lq, L, R) the reference points
-template <typename T, int D, bool FUSED>
+// AT   : element type of `loc` / `attn` (float; the fused kernels also take the 16-bit value type)
+template <typename T, int D, bool FUSED, typename AT>
 __global__ void __launch_bounds__(kThreads)
 msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
-                    const int64_t* __restrict__ lsi, const float* __restrict__ loc,
-                    const float* __restrict__ attn, const float* __restrict__ ref, int R, T* __restrict__ out,
+                    const int64_t* __restrict__ lsi, const AT* __restrict__ loc,
+                    const AT* __restrict__ attn, const float* __restrict__ ref, int R, T* __restrict__ out,
                     int S, int M, int Lq, int L, int P, int total_pairs) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr int G = D / VEC;        // lanes per (b, q, m) pair
@@ -191,8 +249,19 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   const int pair0 = (blockIdx.x * kWarps + warp) * GPW;
   const int nvalid = min(GPW, total_pairs - pair0);
   if (nvalid <= 0) return;
-  stage_in(ws, loc + static_cast<size_t>(pair0) * (2 * LP), attn + static_cast<size_t>(pair0) * LP, nvalid, LP, lane);
+  stage_in<AT>(ws, loc + static_cast<size_t>(pair0) * (2 * LP), attn + static_cast<size_t>(pair0) * LP, nvalid, LP, lane);
+  float4* sref = nullptr;
+  if constexpr (FUSED) {
+    // float4 rows behind the CTA's loc / attn rows (16-byte aligned: every row length is a multiple of 4 floats)
+    sref = reinterpret_cast<float4*>(smem + kWarps * GPW * (ws.loc_stride + ws.attn_stride)) + warp * GPW * L;
+    stage_ref(sref, meta, ref, R, pair0, nvalid, M, L, P, lane);
+  }
   __syncwarp();
+  if constexpr (FUSED) {
+    const bool active = g < nvalid;
+    const int row = active ? g : 0;
+    fused_prepare<G>(ws.loc + row * ws.loc_stride, ws.attn + row * ws.attn_stride, sref + row * L, L, P, c, active);
+  }
   if (g >= nvalid) return;
 
   const int pair = pair0 + g;
@@ -200,10 +269,8 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   const int b = (pair / M) / Lq;
   const uint32_t pix_bytes = static_cast<uint32_t>(M) * D * sizeof(T);        // bytes between neighbouring pixels
   const char* vb = reinterpret_cast<const char*>(value) + (static_cast<size_t>(b) * S * M + m) * (D * sizeof(T)) + c * 16;
-  float* myloc = ws.loc + g * ws.loc_stride;
-  float* myattn = ws.attn + g * ws.attn_stride;
-  if constexpr (FUSED)
-    fused_prepare<G>(myloc, myattn, meta, ref + static_cast<size_t>(pair / M) * L * R, R, L, P, c, group_mask<G>(g));
+  const float* myloc = ws.loc + g * ws.loc_stride;
+  const float* myattn = ws.attn + g * ws.attn_stride;
 
   float acc[VEC];
 #pragma unroll
@@ -276,14 +343,15 @@ __device__ __forceinline__ float f16_accum_scale(const uint32_t* __restrict__ ct
 //               reduction bytes of the fp32 path (the SM->L2 reduction path is what bounds this kernel).
 // FUSED   : `loc` / `attn` hold raw sampling offsets / attention logits, `ref` (N, Lq, L, R) the reference points;
 //           `grad_loc` / `grad_attn` receive the gradients of the raw offsets / logits (see fused_prepare).
-template <typename T, int D, bool GV16, bool FUSED>
+// AT      : element type of `loc` / `attn` / `grad_loc` / `grad_attn` (float; fused kernels also the 16-bit value type)
+template <typename T, int D, bool GV16, bool FUSED, typename AT>
 __global__ void __launch_bounds__(kThreads, BWD_MIN_CTAS)
 msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
-                    const int64_t* __restrict__ lsi, const float* __restrict__ loc,
-                    const float* __restrict__ attn, const float* __restrict__ ref, int R,
+                    const int64_t* __restrict__ lsi, const AT* __restrict__ loc,
+                    const AT* __restrict__ attn, const float* __restrict__ ref, int R,
                     const T* __restrict__ grad_out,
                     float* __restrict__ gv32, __half* __restrict__ gv16, const uint32_t* __restrict__ ctrl,
-                    float* __restrict__ grad_loc, float* __restrict__ grad_attn,
+                    AT* __restrict__ grad_loc, AT* __restrict__ grad_attn,
                     int S, int M, int Lq, int L, int P, int total_pairs, int depth) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr int G = D / VEC;
@@ -310,7 +378,12 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   const int pair0 = (blockIdx.x * kWarps + warp) * GPW;
   const int nvalid = min(GPW, total_pairs - pair0);
   if (nvalid <= 0) return;
-  stage_in(ws, loc + static_cast<size_t>(pair0) * (2 * LP), attn + static_cast<size_t>(pair0) * LP, nvalid, LP, lane);
+  stage_in<AT>(ws, loc + static_cast<size_t>(pair0) * (2 * LP), attn + static_cast<size_t>(pair0) * LP, nvalid, LP, lane);
+  float4* sref = nullptr;
+  if constexpr (FUSED) {
+    sref = reinterpret_cast<float4*>(smem + kWarps * GPW * (ws.loc_stride + 2 * ws.attn_stride)) + warp * GPW * L;
+    stage_ref(sref, meta, ref, R, pair0, nvalid, M, L, P, lane);
+  }
   __syncwarp();
 
   // Lanes of padding groups (tail warp only) stay in the loop so that the full-mask shuffles are legal;
@@ -325,13 +398,11 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   float* myloc = ws.loc + (active ? g : 0) * ws.loc_stride;
   float* myattn = ws.attn + (active ? g : 0) * ws.attn_stride;
   float* mygattn = nullptr;
-  const float* refq = nullptr;
+  const float4* myref = nullptr;
   if constexpr (FUSED) {
     mygattn = ws.gattn + (active ? g : 0) * ws.attn_stride;
-    refq = ref + static_cast<size_t>(pair / M) * L * R;
-    // padding groups shadow row 0 read-only: only the owning group rewrites a row
-    if (active) fused_prepare<G>(myloc, myattn, meta, refq, R, L, P, c, group_mask<G>(g));
-    __syncwarp();
+    myref = sref + (active ? g : 0) * L;
+    fused_prepare<G>(myloc, myattn, myref, L, P, c, active);     // padding groups shadow row 0 read-only
   }
 
   // grad_out of this pair: raw 16 bytes in the value layout (for the dot products) and, for the fp32
@@ -450,7 +521,8 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     if (active && owner >= 0 && lp0 + owner < LP) {
       if constexpr (FUSED) {
         const int lpo = lp0 + owner;
-        *reinterpret_cast<float2*>(myloc + 2 * lpo) = fused_offset_grad(part[0][1], part[0][2], meta, refq, R, lpo / P, P);
+        const float4 rs = myref[level_of(lpo, 1.0f / static_cast<float>(P))];
+        *reinterpret_cast<float2*>(myloc + 2 * lpo) = make_float2(__fmul_rn(part[0][1], rs.z), __fmul_rn(part[0][2], rs.w));
         mygattn[lpo] = part[0][0];        // the softmax output stays in myattn for the chain rule below
       } else {
         *reinterpret_cast<float2*>(myloc + 2 * (lp0 + owner)) = make_float2(part[0][1], part[0][2]);
@@ -460,18 +532,18 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   }
   __syncwarp();
   if constexpr (FUSED) {
-    if (active) {                         // softmax backward over the pair's L*P entries
-      const unsigned gmask = group_mask<G>(g);
+    {                                     // softmax backward over the pair's L*P entries (all lanes: full-mask shuffles)
       float dot = 0.f;
       for (int i = c; i < LP; i += G) dot += mygattn[i] * myattn[i];
 #pragma unroll
-      for (int s = G / 2; s >= 1; s >>= 1) dot += __shfl_xor_sync(gmask, dot, s);
-      for (int i = c; i < LP; i += G) mygattn[i] = __fmul_rn(__fsub_rn(mygattn[i], dot), myattn[i]);
+      for (int s = G / 2; s >= 1; s >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, s);
+      if (active)
+        for (int i = c; i < LP; i += G) mygattn[i] = (mygattn[i] - dot) * myattn[i];
     }
     __syncwarp();
-    stage_out(ws, ws.gattn, grad_loc + static_cast<size_t>(pair0) * (2 * LP), grad_attn + static_cast<size_t>(pair0) * LP, nvalid, LP, lane);
+    stage_out<AT>(ws, ws.gattn, grad_loc + static_cast<size_t>(pair0) * (2 * LP), grad_attn + static_cast<size_t>(pair0) * LP, nvalid, LP, lane);
   } else {
-    stage_out(ws, ws.attn, grad_loc + static_cast<size_t>(pair0) * (2 * LP), grad_attn + static_cast<size_t>(pair0) * LP, nvalid, LP, lane);
+    stage_out<AT>(ws, ws.attn, grad_loc + static_cast<size_t>(pair0) * (2 * LP), grad_attn + static_cast<size_t>(pair0) * LP, nvalid, LP, lane);
   }
 }
 
@@ -715,6 +787,7 @@ struct Problem {
   int total_pairs;
   const float* ref = nullptr;   // fused pre-op: reference points (N, Lq, L, R); nullptr = plain operator
   int R = 0;
+  bool aux16 = false;           // fused pre-op only: offsets / logits (and their gradients) are in the 16-bit value type
 };
 
 static int validate(const Problem& pr, int dtype, int im2col_step) {
@@ -738,11 +811,14 @@ template <typename T> static bool vec_supported(const Problem& pr) {
   return d_ok && static_cast<unsigned long long>(pr.S) * pr.M * pr.D * sizeof(float) < (1ull << 32);
 }
 
+// per warp: GPW rows of loc (2*LP + 4 floats) and attn (LP + 4); fused backward adds a gattn row per pair; fused kernels
+// add the float4 (rx, ry, sx, sy) row of every (pair, level) behind all warps' rows
 template <typename T, int D>
-static size_t vec_smem_bytes(int L, int P, bool fused_bwd = false) {
+static size_t vec_smem_bytes(int L, int P, bool fused = false, bool bwd = false) {
   constexpr int G = D / (16 / static_cast<int>(sizeof(T)));
   constexpr int GPW = 32 / G;
-  return static_cast<size_t>(kWarps) * GPW * ((fused_bwd ? 4 : 3) * L * P + (fused_bwd ? 12 : 8)) * sizeof(float);
+  const bool fb = fused && bwd;
+  return static_cast<size_t>(kWarps) * GPW * ((fb ? 4 : 3) * L * P + (fb ? 12 : 8) + (fused ? 4 * L : 0)) * sizeof(float);
 }
 
 template <typename K>
@@ -751,19 +827,19 @@ static cudaError_t allow_smem(K kernel, size_t bytes) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
 }
 
-template <typename T, int D, bool FUSED>
+template <typename T, int D, bool FUSED, typename AT>
 static int launch_fwd_vec_impl(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
                                const void* loc, const void* attn, void* out, cudaStream_t st) {
   constexpr int GPW = 32 / (D / (16 / static_cast<int>(sizeof(T))));
   const int per_cta = kWarps * GPW;
   const int grid = (pr.total_pairs + per_cta - 1) / per_cta;
-  const size_t smem = vec_smem_bytes<T, D>(pr.L, pr.P);
+  const size_t smem = vec_smem_bytes<T, D>(pr.L, pr.P, FUSED, false);
   if (smem > 200 * 1024) return MSDA_ERR_BAD_SHAPE;
-  cudaError_t e = allow_smem(msda_fwd_vec_kernel<T, D, FUSED>, smem);
+  cudaError_t e = allow_smem(msda_fwd_vec_kernel<T, D, FUSED, AT>, smem);
   if (e != cudaSuccess) return static_cast<int>(e);
   ScopedKernelTimer timer(MSDA_KERNEL_FORWARD, st);
-  msda_fwd_vec_kernel<T, D, FUSED><<<grid, kThreads, smem, st>>>(
-      static_cast<const T*>(value), shapes, lsi, static_cast<const float*>(loc), static_cast<const float*>(attn),
+  msda_fwd_vec_kernel<T, D, FUSED, AT><<<grid, kThreads, smem, st>>>(
+      static_cast<const T*>(value), shapes, lsi, static_cast<const AT*>(loc), static_cast<const AT*>(attn),
       pr.ref, pr.R, static_cast<T*>(out), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs);
   ++g_last_launches, ++g_total_launches;
   return static_cast<int>(cudaGetLastError());
@@ -772,8 +848,11 @@ static int launch_fwd_vec_impl(const Problem& pr, const void* value, const int64
 template <typename T, int D>
 static int launch_fwd_vec(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
                           const void* loc, const void* attn, void* out, cudaStream_t st) {
-  if (pr.ref) return launch_fwd_vec_impl<T, D, true>(pr, value, shapes, lsi, loc, attn, out, st);
-  return launch_fwd_vec_impl<T, D, false>(pr, value, shapes, lsi, loc, attn, out, st);
+  if constexpr (sizeof(T) == 2) {
+    if (pr.ref && pr.aux16) return launch_fwd_vec_impl<T, D, true, T>(pr, value, shapes, lsi, loc, attn, out, st);
+  }
+  if (pr.ref) return launch_fwd_vec_impl<T, D, true, float>(pr, value, shapes, lsi, loc, attn, out, st);
+  return launch_fwd_vec_impl<T, D, false, float>(pr, value, shapes, lsi, loc, attn, out, st);
 }
 
 template <typename T>
@@ -799,35 +878,35 @@ static int launch_fwd(const Problem& pr, const void* value, const int64_t* shape
   return static_cast<int>(cudaGetLastError());
 }
 
-template <typename T, int D, bool FUSED>
+template <typename T, int D, bool FUSED, typename AT>
 static int launch_bwd_vec_impl(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
                                const void* loc, const void* attn, const void* go, float* gv32, __half* gv16,
                                const uint32_t* ctrl, void* gloc, void* gattn, bool use16, int depth, cudaStream_t st) {
   constexpr int GPW = 32 / (D / (16 / static_cast<int>(sizeof(T))));
-  const size_t smem = vec_smem_bytes<T, D>(pr.L, pr.P, FUSED);
+  const size_t smem = vec_smem_bytes<T, D>(pr.L, pr.P, FUSED, true);
   if (smem > 200 * 1024) return MSDA_ERR_BAD_SHAPE;
   const int per_cta = kWarps * GPW;
   const int grid = (pr.total_pairs + per_cta - 1) / per_cta;
   cudaError_t e;
   if constexpr (sizeof(T) == 2) {
     if (use16) {
-      e = allow_smem(msda_bwd_vec_kernel<T, D, true, FUSED>, smem);
+      e = allow_smem(msda_bwd_vec_kernel<T, D, true, FUSED, AT>, smem);
       if (e != cudaSuccess) return static_cast<int>(e);
       ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD, st);
-      msda_bwd_vec_kernel<T, D, true, FUSED><<<grid, kThreads, smem, st>>>(
-          static_cast<const T*>(value), shapes, lsi, static_cast<const float*>(loc), static_cast<const float*>(attn),
-          pr.ref, pr.R, static_cast<const T*>(go), nullptr, gv16, ctrl, static_cast<float*>(gloc),
-          static_cast<float*>(gattn), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth);
+      msda_bwd_vec_kernel<T, D, true, FUSED, AT><<<grid, kThreads, smem, st>>>(
+          static_cast<const T*>(value), shapes, lsi, static_cast<const AT*>(loc), static_cast<const AT*>(attn),
+          pr.ref, pr.R, static_cast<const T*>(go), nullptr, gv16, ctrl, static_cast<AT*>(gloc),
+          static_cast<AT*>(gattn), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth);
       ++g_last_launches, ++g_total_launches;
       return static_cast<int>(cudaGetLastError());
     }
   }
-  e = allow_smem(msda_bwd_vec_kernel<T, D, false, FUSED>, smem);
+  e = allow_smem(msda_bwd_vec_kernel<T, D, false, FUSED, AT>, smem);
   if (e != cudaSuccess) return static_cast<int>(e);
   ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD, st);
-  msda_bwd_vec_kernel<T, D, false, FUSED><<<grid, kThreads, smem, st>>>(
-      static_cast<const T*>(value), shapes, lsi, static_cast<const float*>(loc), static_cast<const float*>(attn),
-      pr.ref, pr.R, static_cast<const T*>(go), gv32, nullptr, nullptr, static_cast<float*>(gloc), static_cast<float*>(gattn),
+  msda_bwd_vec_kernel<T, D, false, FUSED, AT><<<grid, kThreads, smem, st>>>(
+      static_cast<const T*>(value), shapes, lsi, static_cast<const AT*>(loc), static_cast<const AT*>(attn),
+      pr.ref, pr.R, static_cast<const T*>(go), gv32, nullptr, nullptr, static_cast<AT*>(gloc), static_cast<AT*>(gattn),
       pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth);
   ++g_last_launches, ++g_total_launches;
   return static_cast<int>(cudaGetLastError());
@@ -837,9 +916,13 @@ template <typename T, int D>
 static int launch_bwd_vec(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
                           const void* loc, const void* attn, const void* go, float* gv32, __half* gv16,
                           const uint32_t* ctrl, void* gloc, void* gattn, bool use16, int depth, cudaStream_t st) {
+  if constexpr (sizeof(T) == 2) {
+    if (pr.ref && pr.aux16)
+      return launch_bwd_vec_impl<T, D, true, T>(pr, value, shapes, lsi, loc, attn, go, gv32, gv16, ctrl, gloc, gattn, use16, depth, st);
+  }
   if (pr.ref)
-    return launch_bwd_vec_impl<T, D, true>(pr, value, shapes, lsi, loc, attn, go, gv32, gv16, ctrl, gloc, gattn, use16, depth, st);
-  return launch_bwd_vec_impl<T, D, false>(pr, value, shapes, lsi, loc, attn, go, gv32, gv16, ctrl, gloc, gattn, use16, depth, st);
+    return launch_bwd_vec_impl<T, D, true, float>(pr, value, shapes, lsi, loc, attn, go, gv32, gv16, ctrl, gloc, gattn, use16, depth, st);
+  return launch_bwd_vec_impl<T, D, false, float>(pr, value, shapes, lsi, loc, attn, go, gv32, gv16, ctrl, gloc, gattn, use16, depth, st);
 }
 
 template <typename T>
@@ -1059,8 +1142,10 @@ extern "C" int msda_fused_supported(int D, int value_dtype) {
 }
 
 
-static int fused_validate(const Problem& pr, int value_dtype, int ref_dim) {
+static int fused_validate(const Problem& pr, int value_dtype, int ref_dim, int aux_dtype) {
   if (ref_dim != 2 && ref_dim != 4) return MSDA_ERR_FUSED_UNSUPPORTED;
+  if (aux_dtype != MSDA_F32 && !(aux_dtype == value_dtype && (value_dtype == MSDA_BF16 || value_dtype == MSDA_F16)))
+    return MSDA_ERR_FUSED_UNSUPPORTED;
   if (!msda_fused_supported(pr.D, value_dtype)) return MSDA_ERR_FUSED_UNSUPPORTED;
   if (static_cast<unsigned long long>(pr.S) * pr.M * pr.D * sizeof(float) >= (1ull << 32)) return MSDA_ERR_FUSED_UNSUPPORTED;
   return MSDA_OK;
@@ -1070,18 +1155,19 @@ extern "C" int msda_fused_forward(const void* value, const int64_t* spatial_shap
                                   const void* reference_points, int ref_dim, const void* sampling_offsets,
                                   const void* attn_logits, void* output,
                                   int N, int S, int M, int D, int Lq, int L, int P,
-                                  int value_dtype, int im2col_step, void* stream) {
+                                  int value_dtype, int aux_dtype, int im2col_step, void* stream) {
   g_last_launches = 0;
   if (!value || !spatial_shapes || !level_start_index || !reference_points || !sampling_offsets || !attn_logits || !output)
     return MSDA_ERR_NULL_POINTER;
   Problem pr{N, S, M, D, Lq, L, P, 0};
   int v = validate(pr, value_dtype, im2col_step);
   if (v != MSDA_OK) return v;
-  v = fused_validate(pr, value_dtype, ref_dim);
+  v = fused_validate(pr, value_dtype, ref_dim, aux_dtype);
   if (v != MSDA_OK) return v;
   pr.total_pairs = N * Lq * M;
   pr.ref = static_cast<const float*>(reference_points);
   pr.R = ref_dim;
+  pr.aux16 = aux_dtype != MSDA_F32;
   if (!aligned16(value) || !aligned16(sampling_offsets) || !aligned16(attn_logits) || !aligned16(output) ||
       !aligned16(reference_points))
     return MSDA_ERR_MISALIGNED;
@@ -1100,7 +1186,7 @@ extern "C" int msda_fused_backward(const void* value, const int64_t* spatial_sha
                                    void* grad_value, void* grad_sampling_offsets, void* grad_attn_logits,
                                    void* scratch, size_t scratch_bytes,
                                    int N, int S, int M, int D, int Lq, int L, int P,
-                                   int value_dtype, int im2col_step, int flags, void* stream) {
+                                   int value_dtype, int aux_dtype, int im2col_step, int flags, void* stream) {
   g_last_launches = 0;
   if (!value || !spatial_shapes || !level_start_index || !reference_points || !sampling_offsets || !attn_logits ||
       !grad_output || !grad_value || !grad_sampling_offsets || !grad_attn_logits)
@@ -1108,11 +1194,12 @@ extern "C" int msda_fused_backward(const void* value, const int64_t* spatial_sha
   Problem pr{N, S, M, D, Lq, L, P, 0};
   int v = validate(pr, value_dtype, im2col_step);
   if (v != MSDA_OK) return v;
-  v = fused_validate(pr, value_dtype, ref_dim);
+  v = fused_validate(pr, value_dtype, ref_dim, aux_dtype);
   if (v != MSDA_OK) return v;
   pr.total_pairs = N * Lq * M;
   pr.ref = static_cast<const float*>(reference_points);
   pr.R = ref_dim;
+  pr.aux16 = aux_dtype != MSDA_F32;
   if (!aligned16(value) || !aligned16(sampling_offsets) || !aligned16(attn_logits) || !aligned16(grad_output) ||
       !aligned16(grad_value) || !aligned16(grad_sampling_offsets) || !aligned16(grad_attn_logits) ||
       !aligned16(scratch) || !aligned16(reference_points))

@@ -91,3 +91,90 @@ class GradientBucket:
             self._work.wait()
             self.flat.div_(dist.get_world_size())
             self._work = None
+
+
+class GradientBuckets:
+    """Gradients of a module tree as views into one flat buffer, all-reduced group by group *during* backward.
+
+    `groups` is a list of parameter lists (e.g. one per encoder layer, in forward order).  Every parameter's `.grad`
+    is a view into `flat`, so autograd accumulates straight into the bucket (no copy in, no copy out).  A
+    post-accumulate hook counts a group's parameters down; when the last one has its gradient, the group's slice is
+    averaged over the ranks on a side stream (NCCL over NVLink / NVSwitch on the B200 box), overlapping the backward of
+    the layers below it.  `wait()` joins the side stream; `zero()` clears the bucket for the next step.  This is the one
+    exchange a batch-sharded training step of the path has — the operator itself needs none."""
+
+    def __init__(self, groups, device=None):
+        groups = [[p for p in g if p.requires_grad] for g in groups]
+        groups = [g for g in groups if g]
+        params = [p for g in groups for p in g]
+        if not params:
+            raise ValueError("no trainable parameters")
+        self.device = torch.device(device) if device is not None else params[0].device
+        dtype = params[0].dtype
+        self.flat = torch.zeros(sum(p.numel() for p in params), dtype=dtype, device=self.device)
+        self.slices, self._group_of, self._handles = [], {}, []
+        off = 0
+        for gi, g in enumerate(groups):
+            start = off
+            for p in g:
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+                self._group_of[id(p)] = gi
+                self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
+            self.slices.append((start, off))
+        self._sizes = [len(g) for g in groups]
+        self._pending = list(self._sizes)
+        self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self.launched = 0
+
+    def _distributed(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _on_grad(self, p):
+        gi = self._group_of[id(p)]
+        self._pending[gi] -= 1
+        if self._pending[gi] == 0:
+            self._reduce(gi)
+
+    def _reduce(self, gi):
+        self.launched += 1
+        if not self._distributed():
+            return
+        a, b = self.slices[gi]
+        chunk = self.flat[a:b]
+        world = dist.get_world_size()
+        if self.stream is not None:
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))     # the group's gradients are complete
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(chunk, op=dist.ReduceOp.SUM)
+                chunk.div_(world)
+        else:
+            dist.all_reduce(chunk, op=dist.ReduceOp.SUM)
+            chunk.div_(world)
+
+    def wait(self):
+        """Join the reductions; afterwards every rank holds the averaged gradients in `.grad` / `flat`."""
+        if any(n != 0 and n != s for n, s in zip(self._pending, self._sizes)):
+            raise RuntimeError("backward left a gradient group incomplete (unused parameters?)")
+        if self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    def zero(self):
+        if self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        self.flat.zero_()
+        self._pending = list(self._sizes)
+        self.launched = 0
+
+    def remove_hooks(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
+def encoder_gradient_groups(encoder_only):
+    """Gradient groups of an MSDeformAttnTransformerEncoderOnly in the order backward completes them:
+    last layer first, then ... layer 0, then level_embed."""
+    groups = [list(layer.parameters()) for layer in reversed(list(encoder_only.encoder.layers))]
+    groups.append([encoder_only.level_embed])
+    return groups

@@ -23,6 +23,15 @@ CONFIGS = {
                                    dtype=torch.bfloat16, kind="decoder", queries=300, layers=9),
     "cfg5_2048_bf16": dict(shapes=[(256, 256), (128, 128), (64, 64), (32, 32)], batch=16,
                            dtype=torch.bfloat16, kind="encoder", layers=6),
+    # BASELINE.json configs[4]: one batch-sharded training step of the 6-layer pixel-decoder encoder at 2048^2
+    # (forward + backward under bf16 autocast, per-layer NCCL gradient all-reduce, fused AdamW); `batch` is the GLOBAL
+    # batch, split over the ranks (strong scaling).  BASELINE.json gives no batch size: 8 keeps the 1-GPU leg well inside
+    # 180 GB (~10 GB of saved activations per image).
+    "cfg5_train_step_2048": dict(shapes=[(256, 256), (128, 128), (64, 64), (32, 32)], batch=8, dtype=torch.bfloat16,
+                                 kind="train_step", layers=6, d_model=256, heads=8, points=4, d_ffn=2048),
+    # the same step at the cfg3 geometry (1024^2), for quick runs
+    "cfg3_train_step_1024": dict(shapes=[(128, 128), (64, 64), (32, 32), (16, 16)], batch=16, dtype=torch.bfloat16,
+                                 kind="train_step", layers=6, d_model=256, heads=8, points=4, d_ffn=2048),
 }
 
 
@@ -124,3 +133,15 @@ def algorithmic_bytes(N, S, Lq, M, D, L, P, value_bytes, aux_bytes=4):
     V = min(N * S * C, 4 * D * pts) * value_bytes
     O = N * Lq * C * value_bytes
     return dict(points=pts, fwd=V + O + 3 * pts * aux_bytes, bwd=2 * V + O + 6 * pts * aux_bytes)
+
+
+def make_feature_pyramid(shapes, batch, channels=256, seed=1234, device="cuda", pin=False):
+    """Synthetic multi-scale backbone features + positional embeddings, per level (N, C, H_l, W_l) fp32 — what the
+    pixel decoder's input projections hand to MSDeformAttnTransformerEncoderOnly.forward."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    srcs = [torch.randn(batch, channels, h, w, generator=gen, device=device) for h, w in shapes]
+    pos = [torch.randn(batch, channels, h, w, generator=gen, device=device) * 0.1 for h, w in shapes]
+    if pin:
+        srcs = [t.pin_memory() for t in srcs]
+        pos = [t.pin_memory() for t in pos]
+    return srcs, pos
