@@ -579,7 +579,7 @@ msda_absmax_kernel(const T* __restrict__ x, size_t n8, uint32_t* __restrict__ ct
 
 // zero the control block and the rows of the bucketed fp16 accumulator that the device-side layout actually uses
 // (the host only knows the upper bound accum_rows_bound(); for few queries the layout is ~half of it)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 msda_zero_f16_buckets_kernel(uint4* __restrict__ scratch, size_t ctrl_vecs, const int64_t* __restrict__ shapes,
                              const int64_t* __restrict__ lsi, int N, int M, int D, int Lq, int L, int P, int depth) {
   __shared__ LevelMeta meta;
@@ -757,15 +757,45 @@ static size_t f16_scratch_bytes(int N, int S, int M, int D, int Lq, int L, int P
   const long long rows = accum_rows_bound(S, L, Lq, P, depth);
   return kF16CtrlBytes + static_cast<size_t>(N) * static_cast<size_t>(rows) * M * D * sizeof(__half);
 }
-static thread_local int g_last_launches = 0;
-static std::atomic<long long> g_total_launches{0};
+// ---- build layout -----------------------------------------------------------------------------------------
+// This file compiles either as ONE translation unit (no macro: everything below) or, to build in parallel, several
+// times (see __graft_entry__.build): -DMSDA_TU_DTYPE=0|1|2 emits the kernels + launchers of float/double | bfloat16 |
+// float16 by explicit instantiation of launch_fwd<T> / launch_bwd<T>, and -DMSDA_TU_ABI emits the shared host state
+// and the C ABI, which reaches the launchers through `extern template`.
+#if defined(MSDA_TU_DTYPE) || defined(MSDA_TU_ABI)
+#define MSDA_SPLIT_BUILD 1
+#endif
+#if defined(MSDA_SPLIT_BUILD) && !defined(MSDA_TU_ABI)
+#define MSDA_STATE extern
+#else
+#define MSDA_STATE
+#endif
+#ifdef MSDA_SPLIT_BUILD
+#define MSDA_LAUNCHER
+#else
+#define MSDA_LAUNCHER static
+#endif
+
+#if defined(MSDA_SPLIT_BUILD) && !defined(MSDA_TU_ABI)
+extern thread_local int g_last_launches;
+extern std::atomic<long long> g_total_launches;
+#else
+thread_local int g_last_launches = 0;
+std::atomic<long long> g_total_launches{0};
+#endif
 
 // ---- optional per-launch timing of the dominant kernels (bench.py's roofline leg) --------------------
 struct ProfileRecord { cudaEvent_t start, stop; int kind; };
 // process-wide (autograd runs backward on its own thread), guarded by a mutex; off by default
-static std::atomic<bool> g_profile_on{false};
-static std::mutex g_profile_mu;
-static std::vector<ProfileRecord> g_profile;
+#if defined(MSDA_SPLIT_BUILD) && !defined(MSDA_TU_ABI)
+extern std::atomic<bool> g_profile_on;
+extern std::mutex g_profile_mu;
+extern std::vector<ProfileRecord> g_profile;
+#else
+std::atomic<bool> g_profile_on{false};
+std::mutex g_profile_mu;
+std::vector<ProfileRecord> g_profile;
+#endif
 
 struct ScopedKernelTimer {
   cudaStream_t st; cudaEvent_t stop = nullptr; bool on = false;
@@ -856,7 +886,7 @@ static int launch_fwd_vec(const Problem& pr, const void* value, const int64_t* s
 }
 
 template <typename T>
-static int launch_fwd(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
+MSDA_LAUNCHER int launch_fwd(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
                       const void* loc, const void* attn, void* out, cudaStream_t st) {
   if constexpr (!std::is_same<T, double>::value) {
     if (vec_supported<T>(pr)) {
@@ -926,7 +956,7 @@ static int launch_bwd_vec(const Problem& pr, const void* value, const int64_t* s
 }
 
 template <typename T>
-static int launch_bwd(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
+MSDA_LAUNCHER int launch_bwd(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
                       const void* loc, const void* attn, const void* go, void* gv, void* gloc, void* gattn,
                       void* scratch, int flags, cudaStream_t st) {
   const size_t n_value = static_cast<size_t>(pr.N) * pr.S * pr.M * pr.D;
@@ -1018,8 +1048,30 @@ static int launch_bwd(const Problem& pr, const void* value, const int64_t* shape
   return rc;
 }
 
+#ifdef MSDA_SPLIT_BUILD
+#define MSDA_LAUNCHERS_OF(KW, T)                                                                                      \
+  KW template int launch_fwd<T>(const Problem&, const void*, const int64_t*, const int64_t*, const void*, const void*, \
+                                void*, cudaStream_t);                                                                 \
+  KW template int launch_bwd<T>(const Problem&, const void*, const int64_t*, const int64_t*, const void*, const void*, \
+                                const void*, void*, void*, void*, void*, int, cudaStream_t);
+#ifdef MSDA_TU_ABI
+MSDA_LAUNCHERS_OF(extern, float)
+MSDA_LAUNCHERS_OF(extern, double)
+MSDA_LAUNCHERS_OF(extern, __nv_bfloat16)
+MSDA_LAUNCHERS_OF(extern, __half)
+#elif MSDA_TU_DTYPE == 0
+MSDA_LAUNCHERS_OF(, float)
+MSDA_LAUNCHERS_OF(, double)
+#elif MSDA_TU_DTYPE == 1
+MSDA_LAUNCHERS_OF(, __nv_bfloat16)
+#elif MSDA_TU_DTYPE == 2
+MSDA_LAUNCHERS_OF(, __half)
+#endif
+#endif
+
 }  // namespace msda
 
+#if !defined(MSDA_SPLIT_BUILD) || defined(MSDA_TU_ABI)
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
@@ -1220,3 +1272,4 @@ extern "C" int msda_fused_backward(const void* value, const int64_t* spatial_sha
   }
   return MSDA_ERR_BAD_DTYPE;
 }
+#endif  // C ABI translation unit
