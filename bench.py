@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
     ap.add_argument("--fused-preop", action="store_true",
                     help="train-step workloads: fold softmax + sampling-location arithmetic into the kernels")
+    ap.add_argument("--fused-layers", action="store_true",
+                    help="train-step workloads: run every encoder layer as one fused autograd node (implies --fused-preop)")
     return ap.parse_args()
 
 
@@ -381,6 +383,7 @@ def run_train_step(args):
             layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
             layer.self_attn.attention_weights.weight.normal_(0, 0.05)
     pkg.set_fused_preop(enc, args.fused_preop)
+    pkg.set_fused_encoder_layers(enc, args.fused_layers)
     buckets = D.GradientBuckets(D.encoder_gradient_groups(enc), device=dev)
     opt = torch.optim.AdamW(enc.parameters(), lr=1e-5, fused=True)
     host_srcs, host_pos = W.make_feature_pyramid(shapes, count, C, seed=99 + start, device="cpu", pin=True)
@@ -392,8 +395,8 @@ def run_train_step(args):
     def step(from_host=False):
         x = [t.to(dev, non_blocking=True) for t in host_srcs] if from_host else srcs
         buckets.zero()
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            memory, _, _ = enc(x, None, pos)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=not args.fused_layers):
+            memory, _, _ = enc(x, None, pos)       # the fused layers are bf16 by construction
         loss = memory.float().square().mean()
         loss.backward()
         buckets.wait()
@@ -432,7 +435,7 @@ def run_train_step(args):
     records = _lib.profile_collect()
     fwd_ms = [t for t, k in records if k == 1]
     bwd_ms = [t for t, k in records if k == 2]
-    final_loss = float(loss)
+    final_loss = float(loss.detach())
 
     e2e = None
     if not args.no_e2e:
@@ -470,7 +473,8 @@ def run_train_step(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload, "global_batch": global_batch, "per_gpu_batch": count, "layers": layers,
                    "levels": shapes, "queries": S, "heads": M, "head_dim": C // M, "points": P, "d_ffn": cfg["d_ffn"],
-                   "fused_preop": bool(args.fused_preop), "optimizer": "AdamW(fused)", "autocast": "bf16",
+                   "fused_preop": bool(args.fused_preop or args.fused_layers), "fused_layers": bool(args.fused_layers),
+                   "optimizer": "AdamW(fused)", "autocast": "bf16",
                    "parallelism": f"dp{world}", "grad_allreduce_bytes": int(buckets.flat.numel() * 4) if world > 1 else 0,
                    "grad_buckets": len(buckets.slices), "points_per_step": pts_per_step, "final_loss": final_loss,
                    "l2_policy": "activations of one step (GBs) >> 126 MB L2; no flush needed"},

@@ -19,3 +19,4 @@ from .ms_deform_attn_oracle import (  # noqa: F401
     msdeformattn_preop_pytorch,
     ms_deform_attn_fused_oracle_grads,
 )
+from .encoder_layer_oracle import add_layernorm_oracle, colsum_oracle, relu_bwd_colsum_oracle  # noqa: F401,E402

@@ -1,0 +1,199 @@
+"""GPU parity of the encoder-layer glue kernels (include/msda_encoder_b200.h) against float64 CPU restatements, and of the
+fused encoder layer (one autograd node per layer) against the stock layer code.  fp32 outputs are held to 1e-5 of the
+oracle's max, bf16 outputs to one bf16 rounding (4e-3)."""
+import copy
+
+import pytest
+import torch
+
+from oracle import add_layernorm_oracle, colsum_oracle, ms_deform_attn_core_pytorch, relu_bwd_colsum_oracle
+from tests.helpers import rel_to_max
+
+pytestmark = pytest.mark.gpu
+BF16_ULP = 2.0 ** -8
+
+
+@pytest.fixture(scope="module")
+def eops(built_library):
+    assert torch.cuda.is_available()
+    import vision_instance_seg_b200 as pkg
+    pkg.load_library()
+    from vision_instance_seg_b200 import encoder_ops
+    return encoder_ops
+
+
+def test_add_cast(eops):
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(3, 37, 256, generator=g)
+    b = torch.randn(3, 37, 256, generator=g)
+    out = eops.add_cast(a.cuda(), b.cuda())
+    assert out.dtype == torch.bfloat16 and torch.equal(out.cpu(), (a + b).to(torch.bfloat16))
+    with pytest.raises(RuntimeError):
+        eops.add_cast(a, b)                        # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("C", [128, 256, 384, 512, 768, 1024])
+@pytest.mark.parametrize("rows", [1, 13, 4099])
+def test_add_layernorm_forward_backward(eops, C, rows):
+    g = torch.Generator().manual_seed(C + rows)
+    x = torch.randn(rows, C, generator=g) * 2 + 0.5
+    delta = (torch.randn(rows, C, generator=g)).to(torch.bfloat16)
+    gamma = torch.randn(C, generator=g) * 0.5 + 1
+    beta = torch.randn(C, generator=g) * 0.1
+    gy = torch.randn(rows, C, generator=g)
+    gy16 = torch.randn(rows, C, generator=g).to(torch.bfloat16)
+    y, y16, mean, rstd = eops.add_layernorm_forward(x.cuda(), delta.cuda(), gamma.cuda(), beta.cuda(), 1e-5)
+    wy, wmean, wrstd, wdx, wdg, wdb = add_layernorm_oracle(x, delta, gamma, beta, 1e-5, gy.double() + gy16.double())
+    assert rel_to_max(y, wy) < 1e-5 and rel_to_max(mean, wmean) < 1e-5 and rel_to_max(rstd, wrstd) < 1e-5
+    assert torch.equal(y16.cpu(), y.cpu().to(torch.bfloat16))
+    dx, dd, dg, db = eops.add_layernorm_backward(gy.cuda(), gy16.cuda(), x.cuda(), delta.cuda(), mean, rstd, gamma.cuda())
+    assert rel_to_max(dx, wdx) < 1e-5
+    assert rel_to_max(dg, wdg) < 2e-5 and rel_to_max(db, wdb) < 2e-5
+    assert torch.equal(dd.cpu(), dx.cpu().to(torch.bfloat16))
+    # optional operands: no delta, only one of the two incoming gradients, no bf16 outputs
+    y2, none16, mean2, rstd2 = eops.add_layernorm_forward(x.cuda(), None, gamma.cuda(), beta.cuda(), 1e-5, want16=False)
+    w2 = add_layernorm_oracle(x, None, gamma, beta, 1e-5, gy16.double())
+    assert none16 is None and rel_to_max(y2, w2[0]) < 1e-5
+    dx2, dd2, dg2, db2 = eops.add_layernorm_backward(None, gy16.cuda(), x.cuda(), None, mean2, rstd2, gamma.cuda(), want_ddelta=False)
+    assert dd2 is None and rel_to_max(dx2, w2[3]) < 1e-5 and rel_to_max(dg2, w2[4]) < 2e-5 and rel_to_max(db2, w2[5]) < 2e-5
+
+
+@pytest.mark.parametrize("C", [8, 48, 128, 256, 384, 2048])
+def test_colsum_and_segments(eops, C):
+    g = torch.Generator().manual_seed(C)
+    t = torch.randn(3, 301, C, generator=g).to(torch.bfloat16)
+    assert rel_to_max(eops.colsum(t.cuda()), colsum_oracle(t)) < 1e-5
+    assert rel_to_max(eops.colsum(t.cuda(), 17, 123), colsum_oracle(t, 17, 123)) < 1e-5
+    assert rel_to_max(eops.colsum(t.cuda(), 300, 301), colsum_oracle(t, 300, 301)) < 1e-5
+    big = torch.randn(20011, C, generator=g).to(torch.bfloat16)
+    assert rel_to_max(eops.colsum(big.cuda()), colsum_oracle(big)) < 1e-5
+
+
+@pytest.mark.parametrize("C", [256, 2048])
+def test_relu_bwd_colsum(eops, C):
+    g = torch.Generator().manual_seed(C + 1)
+    h = torch.relu(torch.randn(1237, C, generator=g)).to(torch.bfloat16)
+    grad = torch.randn(1237, C, generator=g).to(torch.bfloat16)
+    masked, sums = relu_bwd_colsum_oracle(grad, h)
+    gg = grad.cuda().clone()
+    out = eops.relu_bwd_colsum(gg, h.cuda())
+    assert torch.equal(gg.cpu().double(), masked)
+    assert rel_to_max(out, sums) < 1e-5
+
+
+def test_shape_validation(eops):
+    x = torch.randn(4, 200, device="cuda")
+    with pytest.raises(RuntimeError):
+        eops.add_layernorm_forward(x, None, torch.ones(200, device="cuda"), torch.zeros(200, device="cuda"), 1e-5)
+    with pytest.raises(RuntimeError):
+        eops.colsum(torch.randn(4, 20, device="cuda").to(torch.bfloat16))
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused encoder layers
+# ---------------------------------------------------------------------------------------------------
+class _OracleFunction:
+    @staticmethod
+    def apply(value, shapes, lsi, loc, attn, im2col_step):
+        return ms_deform_attn_core_pytorch(value, shapes, loc, attn)
+
+
+def _pyramid(shapes, N, C, seed, padded):
+    g = torch.Generator().manual_seed(seed)
+    srcs = [torch.randn(N, C, h, w, generator=g) for h, w in shapes]
+    pos = [torch.randn(N, C, h, w, generator=g) * 0.1 for h, w in shapes]
+    masks = [torch.zeros(N, h, w, dtype=torch.bool) for h, w in shapes]
+    if padded:
+        for m in masks:
+            m[1, :, (m.shape[2] * 3) // 4:] = True
+            m[1, (m.shape[1] * 2) // 3:, :] = True
+    return srcs, masks, pos
+
+
+def _rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("padded", [False, True])
+def test_fused_encoder_layers_forward_matches_fp32_oracle(eops, monkeypatch, padded):
+    """Forward of the fused layers (bf16 GEMM operands, fp32 residual stream) against the same encoder in float32 on the
+    CPU with the oracle core: the north_star bf16 tolerance, 2e-2 of the output's max."""
+    import vision_instance_seg_b200 as pkg
+    from vision_instance_seg_b200.modules import encoder as E
+    from vision_instance_seg_b200.modules import ms_deform_attn as MOD
+    torch.manual_seed(11)
+    enc_cpu = E.MSDeformAttnTransformerEncoderOnly(d_model=128, nhead=4, num_encoder_layers=2, dim_feedforward=256,
+                                                   dropout=0.0, num_feature_levels=3, enc_n_points=4)
+    with torch.no_grad():
+        for layer in enc_cpu.encoder.layers:
+            layer.self_attn.sampling_offsets.weight.normal_(0, 0.02)
+            layer.self_attn.attention_weights.weight.normal_(0, 0.2)
+    enc_gpu = copy.deepcopy(enc_cpu).cuda()
+    assert pkg.set_fused_encoder_layers(enc_gpu, True) == 1
+    shapes = [(12, 20), (6, 10), (3, 5)]
+    srcs, masks, pos = _pyramid(shapes, 2, 128, 4, padded)
+    monkeypatch.setattr(MOD, "MSDeformAttnFunction", _OracleFunction)
+    with torch.no_grad():
+        mem_c, _, _ = enc_cpu(srcs, masks, pos)
+    monkeypatch.undo()
+    lib = pkg.load_library()
+    n0 = lib.msda_total_launch_count()
+    with torch.no_grad():
+        mem_g, _, _ = enc_gpu([s.cuda() for s in srcs], [m.cuda() for m in masks], [p.cuda() for p in pos])
+    torch.cuda.synchronize()
+    assert lib.msda_total_launch_count() - n0 >= 2               # the sampling kernels ran inside the fused nodes
+    assert mem_g.dtype == torch.float32 and rel_to_max(mem_g, mem_c) < 2e-2
+
+
+@pytest.mark.parametrize("padded", [False, True])
+def test_fused_encoder_layers_gradients_as_good_as_stock_autocast(eops, padded):
+    """Gradients through a stack of deformable-attention layers are ill-conditioned in bf16 (a sampling point that
+    crosses a pixel line flips a bilinear derivative), so the bar is relative: against the float32 run of the same
+    module on the GPU, the fused layers must be as close as stock torch under bf16 autocast is (relative L2 error, every
+    input and parameter gradient), and close to it in absolute terms."""
+    import vision_instance_seg_b200 as pkg
+    from vision_instance_seg_b200.modules import encoder as E
+    torch.manual_seed(2)
+    enc = E.MSDeformAttnTransformerEncoderOnly(d_model=256, nhead=8, num_encoder_layers=3, dim_feedforward=512,
+                                               dropout=0.0, num_feature_levels=3, enc_n_points=4).cuda()
+    with torch.no_grad():
+        for layer in enc.encoder.layers:
+            layer.self_attn.sampling_offsets.weight.normal_(0, 0.02)
+            layer.self_attn.attention_weights.weight.normal_(0, 0.2)
+    shapes = [(36, 30), (18, 15), (9, 8)]
+    srcs, masks, pos = _pyramid(shapes, 2, 256, 8, padded)
+    srcs = [s.cuda() for s in srcs]
+    pos = [p.cuda() for p in pos]
+    masks = [m.cuda() for m in masks]
+    res, gout = {}, None
+    for mode in ("fp32", "autocast", "fused"):
+        pkg.set_fused_encoder_layers(enc, mode == "fused")
+        enc.zero_grad()
+        xs = [s.clone().requires_grad_(True) for s in srcs]
+        if mode == "autocast":
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                mem, _, _ = enc(xs, masks, pos)
+        else:
+            mem, _, _ = enc(xs, masks, pos)
+        gout = torch.randn_like(mem.float()) if gout is None else gout
+        mem.float().backward(gout)
+        res[mode] = dict(mem=mem.detach().float(), **{f"src{i}": x.grad for i, x in enumerate(xs)},
+                         **{n: p.grad.clone() for n, p in enc.named_parameters()})
+    assert rel_to_max(res["fused"]["mem"], res["fp32"]["mem"]) < 2e-2
+    for k, want in res["fp32"].items():
+        e_fused, e_auto = _rel_l2(res["fused"][k], want), _rel_l2(res["autocast"][k], want)
+        assert e_fused < 1.5 * e_auto + 2e-3, f"{k}: fused {e_fused:.3e} vs autocast {e_auto:.3e}"
+        assert e_fused < 0.3, f"{k}: fused {e_fused:.3e}"
+
+
+def test_fused_layers_fall_back_to_stock_code_when_unsupported(eops):
+    import vision_instance_seg_b200 as pkg
+    from vision_instance_seg_b200.modules import encoder as E
+    enc = E.MSDeformAttnTransformerEncoderOnly(d_model=64, nhead=4, num_encoder_layers=1, dim_feedforward=128,
+                                               dropout=0.0, num_feature_levels=2, enc_n_points=2).cuda()     # d_model 64: stock path
+    pkg.set_fused_encoder_layers(enc, True)
+    srcs = [torch.randn(1, 64, 8, 8, device="cuda"), torch.randn(1, 64, 4, 4, device="cuda")]
+    mem, _, _ = enc(srcs, None, [torch.zeros_like(s) for s in srcs])
+    mem.sum().backward()
+    assert enc.level_embed.grad is not None and torch.isfinite(mem).all()

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_functions():
-    text = open(os.path.join(ROOT, "include", "msda_b200.h")).read()
+    text = "\n".join(open(os.path.join(ROOT, "include", h)).read() for h in ("msda_b200.h", "msda_encoder_b200.h"))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(msda_[a-z0-9_]+)\s*\(", text)))
 
@@ -25,7 +25,7 @@ def test_header_declares_and_library_exports_every_symbol(built_library):
     assert set(declared) == set(_lib.EXPORTED_SYMBOLS), (declared, _lib.EXPORTED_SYMBOLS)
     lib = ctypes.CDLL(built_library)
     for name in declared:
-        assert hasattr(lib, name), f"{name} declared in include/msda_b200.h but not exported"
+        assert hasattr(lib, name), f"{name} declared in include/*.h but not exported"
     assert pkg.load_library().msda_abi_version() == 3
 
 

@@ -13,13 +13,15 @@ cfg = W.CONFIGS["cfg3_train_step_1024"]
 torch.manual_seed(0)
 enc = MSDeformAttnTransformerEncoderOnly(256, 8, 6, 2048, 0.0, "relu", 4, 4).to(dev)
 pkg.set_fused_preop(enc, fused)
+layers = "--fused-layers" in sys.argv
+pkg.set_fused_encoder_layers(enc, layers)
 buckets = D.GradientBuckets(D.encoder_gradient_groups(enc), device=dev)
 opt = torch.optim.AdamW(enc.parameters(), lr=1e-5, fused=True)
 srcs, pos = W.make_feature_pyramid(cfg["shapes"], 16, 256, device=dev)
 
 def step():
     buckets.zero()
-    with torch.autocast("cuda", dtype=torch.bfloat16):
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=not layers):
         mem, _, _ = enc(srcs, None, pos)
     mem.float().square().mean().backward()
     buckets.wait()

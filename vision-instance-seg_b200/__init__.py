@@ -19,7 +19,7 @@ the built library or without a CUDA device raises.
 from . import MultiScaleDeformableAttention  # noqa: F401
 from ._lib import library_path, load_library  # noqa: F401
 from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction  # noqa: F401
-from .modules import MSDeformAttn, set_fused_preop  # noqa: F401
+from .modules import MSDeformAttn, set_fused_encoder_layers, set_fused_preop  # noqa: F401
 
 __all__ = ["MSDeformAttn", "MSDeformAttnFunction", "MSDeformAttnFusedFunction", "MultiScaleDeformableAttention",
-           "set_fused_preop", "load_library", "library_path"]
+           "set_fused_preop", "set_fused_encoder_layers", "load_library", "library_path"]

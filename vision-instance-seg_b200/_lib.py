@@ -38,6 +38,14 @@ EXPORTED_SYMBOLS = (
     "msda_fused_supported",
     "msda_fused_forward",
     "msda_fused_backward",
+    # include/msda_encoder_b200.h
+    "msda_enc_add_cast",
+    "msda_enc_add_layernorm_forward",
+    "msda_enc_add_layernorm_backward_scratch_bytes",
+    "msda_enc_add_layernorm_backward",
+    "msda_enc_colsum_scratch_bytes",
+    "msda_enc_colsum",
+    "msda_enc_relu_bwd_colsum",
 )
 
 
@@ -67,6 +75,21 @@ def _declare(lib):
     lib.msda_fused_backward.restype = i
     lib.msda_fused_backward.argtypes = [vp, i64p, i64p, vp, i, vp, vp, vp, vp, vp, vp, vp, sz,
                                         i, i, i, i, i, i, i, i, i, i, i, vp]
+    ll, fl = ctypes.c_longlong, ctypes.c_float
+    lib.msda_enc_add_cast.restype = i
+    lib.msda_enc_add_cast.argtypes = [vp, vp, vp, sz, vp]
+    lib.msda_enc_add_layernorm_forward.restype = i
+    lib.msda_enc_add_layernorm_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ll, i, fl, vp]
+    lib.msda_enc_add_layernorm_backward_scratch_bytes.restype = sz
+    lib.msda_enc_add_layernorm_backward_scratch_bytes.argtypes = [i]
+    lib.msda_enc_add_layernorm_backward.restype = i
+    lib.msda_enc_add_layernorm_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, ll, i, vp]
+    lib.msda_enc_colsum_scratch_bytes.restype = sz
+    lib.msda_enc_colsum_scratch_bytes.argtypes = [i]
+    lib.msda_enc_colsum.restype = i
+    lib.msda_enc_colsum.argtypes = [vp, vp, vp, sz, ll, ll, ll, ll, i, vp]
+    lib.msda_enc_relu_bwd_colsum.restype = i
+    lib.msda_enc_relu_bwd_colsum.argtypes = [vp, vp, vp, vp, sz, ll, i, vp]
     lib.msda_total_launch_count.restype = ctypes.c_longlong
     lib.msda_total_launch_count.argtypes = []
     lib.msda_profile_enable.restype = i

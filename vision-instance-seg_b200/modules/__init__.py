@@ -1,3 +1,3 @@
 from .ms_deform_attn import MSDeformAttn, set_fused_preop  # noqa: F401
 from .encoder import (MSDeformAttnTransformerEncoder, MSDeformAttnTransformerEncoderLayer,  # noqa: F401
-                      MSDeformAttnTransformerEncoderOnly)
+                      MSDeformAttnTransformerEncoderOnly, set_fused_encoder_layers)

@@ -66,7 +66,22 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
         return self.forward_ffn(src)
 
 
+def set_fused_encoder_layers(module: nn.Module, enabled: bool = True) -> int:
+    """Opt-in: run every encoder layer below ``module`` as one fused autograd node
+    (``modules/fused_encoder_layer.py``: bf16 GEMM operands, fp32 residual stream, glue kernels of
+    include/msda_encoder_b200.h).  Returns how many encoders were switched."""
+    n = 0
+    for m in module.modules():
+        if isinstance(m, MSDeformAttnTransformerEncoder):
+            m.fused_layers = bool(enabled)
+            n += 1
+    return n
+
+
 class MSDeformAttnTransformerEncoder(nn.Module):
+    #: opt-in fused layers; the constructor signature stays upstream's (flip with ``set_fused_encoder_layers``)
+    fused_layers = False
+
     def __init__(self, encoder_layer, num_layers):
         super().__init__()
         self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
@@ -87,9 +102,31 @@ class MSDeformAttnTransformerEncoder(nn.Module):
         reference_points = torch.cat(reference_points_list, 1)
         return reference_points[:, :, None] * valid_ratios[:, None]
 
-    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None):
+    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None,
+                level_embed=None):
+        """``level_embed`` (fused layers only): when given, ``pos`` is taken as a constant that already contains it and
+        the level-embedding gradient is produced by the fused layers themselves (segmented column sums)."""
         output = src
         reference_points = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device)
+        if self.fused_layers and pos is not None:
+            from .fused_encoder_layer import fused_layer_forward, fused_layer_supported
+            if all(fused_layer_supported(layer, src, reference_points) for layer in self.layers):
+                sizes = [int(h) * int(w) for h, w in spatial_shapes.tolist()]
+                bounds, a = [], 0
+                for n in sizes:
+                    bounds.append((a, a + n))
+                    a += n
+                reference_points = reference_points.contiguous()
+                pos_const = pos.detach().contiguous()
+                if level_embed is None and pos.requires_grad:
+                    raise RuntimeError("fused encoder layers treat `pos` as a constant: pass level_embed separately")
+                out32 = src.contiguous()
+                out16 = out32.to(torch.bfloat16)
+                for i, layer in enumerate(self.layers):
+                    out32, out16 = fused_layer_forward(layer, out32, out16, pos_const, level_embed, reference_points,
+                                                       spatial_shapes, level_start_index, padding_mask, bounds,
+                                                       want16=i + 1 < len(self.layers))
+                return out32
         for layer in self.layers:
             output = layer(output, pos, reference_points, spatial_shapes, level_start_index, padding_mask)
         return output
@@ -143,8 +180,10 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         spatial_shapes = torch.as_tensor(spatial_shapes, dtype=torch.long, device=src_flatten.device)
         level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
+        # level_embed is handed over separately for the fused layers, which take the positional term as a constant and
+        # return level_embed's gradient themselves; the stock layers ignore it and differentiate through `pos`
         memory = self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios, lvl_pos_embed_flatten,
-                              mask_flatten if use_masks else None)
+                              mask_flatten if use_masks else None, level_embed=self.level_embed)
         return memory, spatial_shapes, level_start_index
 
 
