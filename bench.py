@@ -484,6 +484,15 @@ def run_train_step(args):
     return 0
 
 
+def _shutdown():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -498,9 +507,12 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
     from vision_instance_seg_b200 import workloads as W
-    if W.CONFIGS[args.workload]["kind"] == "train_step":
-        return run_train_step(args)
-    return run_b200(args)
+    try:
+        if W.CONFIGS[args.workload]["kind"] == "train_step":
+            return run_train_step(args)
+        return run_b200(args)
+    finally:
+        _shutdown()
 
 
 if __name__ == "__main__":
