@@ -197,6 +197,7 @@ def run_b200(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = D.bind_to_gpu_numa_node(local_rank) if world > 1 else "single process: unbound"
     lib = pkg.load_library()          # raises if the CUDA library is missing: no fallback
 
     cfg = W.CONFIGS[args.workload]
@@ -342,7 +343,7 @@ def run_b200(args):
         "config": {"workload": args.workload, "per_gpu_batch": batch, "global_batch": batch * world, "layers": layers,
                    "levels": cfg["shapes"], "queries": Lq, "heads": M, "head_dim": Dh, "points": P,
                    "aux_dtype": "f32", "points_per_step_per_gpu": pts_per_step, "parallelism": f"dp{world}",
-                   "grad_allreduce_bytes": D.ENCODER_GRAD_ELEMENTS * 4 if world > 1 else 0,
+                   "grad_allreduce_bytes": D.ENCODER_GRAD_ELEMENTS * 4 if world > 1 else 0, "cpu_binding_rank0": numa,
                    "l2_policy": f"{layers} independent input sets ({layers * (ab['fwd'] + ab['bwd']) / 1e9:.1f} GB touched per step) >> 126 MB L2; no flush needed"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
     }

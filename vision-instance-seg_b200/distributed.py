@@ -34,6 +34,33 @@ def init_process_group(backend: str | None = None):
     return rank, local_rank, world
 
 
+def bind_to_gpu_numa_node(local_rank: int) -> str:
+    """Best effort: pin this process (and therefore the first-touch placement of the pinned host buffers it allocates
+    afterwards) to the CPUs that are local to GPU `local_rank`'s PCIe root, read from sysfs.  With one process per GPU and
+    host-resident operands (bench.py's `e2e` leg) this keeps every rank's H2D / D2H traffic on its own socket.  Returns a
+    short description of what was done; never raises."""
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return f"gpu {bus}: local cpus {text or '?'} (no change)"
+        os.sched_setaffinity(0, cpus)
+        return f"gpu {bus}: bound to cpus {text}"
+    except Exception as exc:      # no sysfs, no permission, older torch: run unbound
+        return f"unbound ({type(exc).__name__})"
+
+
 def shard_batch(global_batch: int, world: int, rank: int):
     """Contiguous image range [start, start + count) owned by `rank` (strong scaling of a fixed global batch);
     remainders go to the lowest ranks."""
