@@ -8,8 +8,18 @@ import torch
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def golden_cases():
+def _all_golden():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def golden_cases():
+    """Operator-level fixtures (tests/golden/make_golden.py)."""
+    return [n for n in _all_golden() if not n.startswith("module_")]
+
+
+def module_golden_cases():
+    """Module-level fixtures (tests/golden/make_golden_module.py): whole MSDeformAttn.forward incl. the pre-op."""
+    return [n for n in _all_golden() if n.startswith("module_")]
 
 
 def load_golden(name):

@@ -5,7 +5,7 @@ import torch
 
 from oracle import ms_deform_attn_core_pytorch, ms_deform_attn_oracle_grads, ms_deform_attn_scalar_numpy
 from oracle import c_oracle
-from tests.helpers import golden_cases, load_golden, random_problem, rel_to_max
+from tests.helpers import golden_cases, load_golden, module_golden_cases, random_problem, rel_to_max
 
 
 @pytest.mark.parametrize("name", golden_cases())
@@ -85,3 +85,33 @@ def test_empty_attention_and_out_of_range_points_give_zero():
     assert float(ms_deform_attn_core_pytorch(value, ss, loc, attn).abs().max()) == 0.0
     gv, gl, ga = c_oracle.backward(value.numpy(), ss.numpy(), lsi.numpy(), loc.numpy(), attn.numpy(), go.numpy())
     assert np.all(gv == 0) and np.all(gl == 0) and np.all(ga == 0)
+
+
+@pytest.mark.parametrize("name", module_golden_cases())
+def test_preop_oracle_composition_matches_module_golden(name):
+    """Pins oracle.msdeformattn_preop_pytorch (softmax + sampling-location arithmetic, 2-d and 4-d references) together
+    with the core against whole-module vectors produced by transformers' independent MSDeformAttn module."""
+    import torch.nn.functional as F
+    from oracle import msdeformattn_preop_pytorch
+    g = load_golden(name)
+    t = {k: torch.from_numpy(v) if isinstance(v, np.ndarray) and v.ndim else v for k, v in g.items()}
+    M, P = int(g["heads"]), int(g["points"])
+    L = t["shapes"].shape[0]
+    prm = {k[len("param."):]: t[k].clone().requires_grad_(True) for k in t if k.startswith("param.")}
+    query = t["query"].clone().requires_grad_(True)
+    src = t["src"].clone().requires_grad_(True)
+    N, Lq, C = query.shape
+    S = src.shape[1]
+    value = F.linear(src, prm["value_proj.weight"], prm["value_proj.bias"])
+    if bool(g["masked"]):
+        value = value.masked_fill(t["padding"][..., None], 0.0)
+    off = F.linear(query, prm["sampling_offsets.weight"], prm["sampling_offsets.bias"]).view(N, Lq, M, L, P, 2)
+    logits = F.linear(query, prm["attention_weights.weight"], prm["attention_weights.bias"]).view(N, Lq, M, L * P)
+    loc, aw = msdeformattn_preop_pytorch(t["ref"], off, logits, t["shapes"])
+    core = ms_deform_attn_core_pytorch(value.view(N, S, M, C // M), t["shapes"], loc, aw)
+    out = F.linear(core, prm["output_proj.weight"], prm["output_proj.bias"])
+    out.backward(t["grad_out"])
+    assert rel_to_max(out, g["out"]) < 1e-12
+    assert rel_to_max(query.grad, g["grad_query"]) < 1e-11 and rel_to_max(src.grad, g["grad_src"]) < 1e-11
+    for k, p in prm.items():
+        assert rel_to_max(p.grad, g["grad." + k]) < 1e-11, k
