@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
     ap.add_argument("--fused-preop", action="store_true",
                     help="train-step workloads: fold softmax + sampling-location arithmetic into the kernels")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="train-step workloads: capture forward + backward + all-reduce + optimizer in one CUDA graph")
     ap.add_argument("--fused-layers", action="store_true",
                     help="train-step workloads: run every encoder layer as one fused autograd node (implies --fused-preop)")
     return ap.parse_args()
@@ -386,15 +388,14 @@ def run_train_step(args):
     pkg.set_fused_preop(enc, args.fused_preop)
     pkg.set_fused_encoder_layers(enc, args.fused_layers)
     buckets = D.GradientBuckets(D.encoder_gradient_groups(enc), device=dev)
-    opt = torch.optim.AdamW(enc.parameters(), lr=1e-5, fused=True)
+    opt = torch.optim.AdamW(enc.parameters(), lr=1e-5, fused=True, capturable=args.cuda_graph)
     host_srcs, host_pos = W.make_feature_pyramid(shapes, count, C, seed=99 + start, device="cpu", pin=True)
     srcs = [t.to(dev) for t in host_srcs]
     pos = [t.to(dev) for t in host_pos]
     pts_per_step = global_batch * S * M * L * P * layers
     loss_host = torch.zeros(1).pin_memory()
 
-    def step(from_host=False):
-        x = [t.to(dev, non_blocking=True) for t in host_srcs] if from_host else srcs
+    def step_body(x):
         buckets.zero()
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=not args.fused_layers):
             memory, _, _ = enc(x, None, pos)       # the fused layers are bf16 by construction
@@ -402,8 +403,21 @@ def run_train_step(args):
         loss.backward()
         buckets.wait()
         opt.step()
+        return loss.detach()
+
+    graph, graph_loss = None, None
+
+    def step(from_host=False):
+        if graph is not None:                   # static inputs: refresh them in place, then replay the captured step
+            if from_host:
+                for d, h in zip(srcs, host_srcs):
+                    d.copy_(h, non_blocking=True)
+            graph.replay()
+            loss = graph_loss
+        else:
+            loss = step_body([t.to(dev, non_blocking=True) for t in host_srcs] if from_host else srcs)
         if from_host:
-            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            loss_host.copy_(loss.reshape(1), non_blocking=True)
         return loss
 
     def barrier():
@@ -411,6 +425,19 @@ def run_train_step(args):
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
 
+    if args.cuda_graph:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):           # warm up off the default stream (allocator, cuBLAS workspaces, NCCL)
+            for _ in range(3):
+                step_body(srcs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        barrier()
+        launches_a = lib.msda_total_launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            graph_loss = step_body(srcs)
+        launches_per_replay = lib.msda_total_launch_count() - launches_a
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -418,7 +445,7 @@ def run_train_step(args):
     if sampler:
         sampler.start()
         time.sleep(0.3)
-    lib.msda_profile_enable(1)
+    lib.msda_profile_enable(0 if args.cuda_graph else 1)     # event pairs cannot be read back out of a captured graph
     launches0 = lib.msda_total_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -431,6 +458,8 @@ def run_train_step(args):
     t1 = time.time()
     lib.msda_profile_enable(0)
     launches = lib.msda_total_launch_count() - launches0
+    if args.cuda_graph:
+        launches = launches_per_replay * args.steps          # replayed launches do not pass through the library's counter
     clocks = sampler.stop(t0, t1) if sampler else None
     ms_per_step = D.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
     records = _lib.profile_collect()
@@ -475,6 +504,7 @@ def run_train_step(args):
         "config": {"workload": args.workload, "global_batch": global_batch, "per_gpu_batch": count, "layers": layers,
                    "levels": shapes, "queries": S, "heads": M, "head_dim": C // M, "points": P, "d_ffn": cfg["d_ffn"],
                    "fused_preop": bool(args.fused_preop or args.fused_layers), "fused_layers": bool(args.fused_layers),
+                   "cuda_graph": bool(args.cuda_graph),
                    "optimizer": "AdamW(fused)", "autocast": "bf16",
                    "parallelism": f"dp{world}", "grad_allreduce_bytes": int(buckets.flat.numel() * 4) if world > 1 else 0,
                    "grad_buckets": len(buckets.slices), "points_per_step": pts_per_step, "final_loss": final_loss,

@@ -70,7 +70,7 @@ def test_flattening_metadata_without_operator_call():
     seen = {}
 
     class FakeEncoder(torch.nn.Module):
-        def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None, level_embed=None):
+        def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None, level_embed=None, spatial_shapes_list=None):
             seen.update(src=src, ss=spatial_shapes, lsi=level_start_index, vr=valid_ratios, pos=pos, mask=padding_mask)
             return src
 

@@ -153,6 +153,10 @@ class GradientBuckets:
         self._pending = list(self._sizes)
         self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         self.launched = 0
+        # True while the side stream holds reductions the main stream has not joined yet.  Joining only then keeps the
+        # class usable inside a CUDA-graph capture: a capturing stream may not wait on a stream that was never forked
+        # from it (cudaErrorStreamCaptureIsolation).
+        self._side_pending = False
 
     def _distributed(self):
         return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
@@ -175,6 +179,7 @@ class GradientBuckets:
             with torch.cuda.stream(self.stream):
                 dist.all_reduce(chunk, op=dist.ReduceOp.SUM)
                 chunk.div_(world)
+            self._side_pending = True
         else:
             dist.all_reduce(chunk, op=dist.ReduceOp.SUM)
             chunk.div_(world)
@@ -183,12 +188,15 @@ class GradientBuckets:
         """Join the reductions; afterwards every rank holds the averaged gradients in `.grad` / `flat`."""
         if any(n != 0 and n != s for n, s in zip(self._pending, self._sizes)):
             raise RuntimeError("backward left a gradient group incomplete (unused parameters?)")
-        if self.stream is not None:
+        self._join()
+
+    def _join(self):
+        if self.stream is not None and self._side_pending:
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
+            self._side_pending = False
 
     def zero(self):
-        if self.stream is not None:
-            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        self._join()
         self.flat.zero_()
         self._pending = list(self._sizes)
         self.launched = 0

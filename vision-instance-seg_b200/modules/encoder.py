@@ -90,7 +90,8 @@ class MSDeformAttnTransformerEncoder(nn.Module):
     @staticmethod
     def get_reference_points(spatial_shapes, valid_ratios, device):
         """(N, S, L, 2): centre of every pixel of every level, normalised by that level's valid extent, then
-        expressed in each sampled level's padded frame."""
+        expressed in each sampled level's padded frame.  ``spatial_shapes``: the (L, 2) tensor (read back with one
+        device->host sync, as upstream does) or a Python list of (H, W) (no sync: CUDA-graph capturable)."""
         reference_points_list = []
         for lvl, (H_, W_) in enumerate(spatial_shapes.tolist() if isinstance(spatial_shapes, torch.Tensor) else spatial_shapes):
             ref_y, ref_x = torch.meshgrid(torch.linspace(0.5, H_ - 0.5, H_, dtype=torch.float32, device=device),
@@ -103,15 +104,18 @@ class MSDeformAttnTransformerEncoder(nn.Module):
         return reference_points[:, :, None] * valid_ratios[:, None]
 
     def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None,
-                level_embed=None):
+                level_embed=None, spatial_shapes_list=None):
         """``level_embed`` (fused layers only): when given, ``pos`` is taken as a constant that already contains it and
-        the level-embedding gradient is produced by the fused layers themselves (segmented column sums)."""
+        the level-embedding gradient is produced by the fused layers themselves (segmented column sums).
+        ``spatial_shapes_list``: the same shapes as Python ints; when given nothing here reads ``spatial_shapes`` back from
+        the device, which keeps the whole forward free of host syncs (CUDA-graph capture)."""
         output = src
-        reference_points = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device)
+        shapes_host = spatial_shapes_list if spatial_shapes_list is not None else spatial_shapes.tolist()
+        reference_points = self.get_reference_points(shapes_host, valid_ratios, device=src.device)
         if self.fused_layers and pos is not None:
             from .fused_encoder_layer import fused_layer_forward, fused_layer_supported
             if all(fused_layer_supported(layer, src, reference_points) for layer in self.layers):
-                sizes = [int(h) * int(w) for h, w in spatial_shapes.tolist()]
+                sizes = [int(h) * int(w) for h, w in shapes_host]
                 bounds, a = [], 0
                 for n in sizes:
                     bounds.append((a, a + n))
@@ -177,13 +181,21 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         src_flatten = torch.cat(src_flatten, 1)
         mask_flatten = torch.cat(mask_flatten, 1)
         lvl_pos_embed_flatten = torch.cat(lvl_pos_embed_flatten, 1)
-        spatial_shapes = torch.as_tensor(spatial_shapes, dtype=torch.long, device=src_flatten.device)
-        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+        shapes_list = [tuple(s) for s in spatial_shapes]
+        # the two int64 metadata tensors are cached per (shapes, device): no pageable host->device copy per call, which a
+        # CUDA-graph capture would reject
+        key = (tuple(shapes_list), str(src_flatten.device))
+        cache = self.__dict__.setdefault("_shape_cache", {})
+        if key not in cache:
+            ss = torch.as_tensor(spatial_shapes, dtype=torch.long, device=src_flatten.device)
+            cache[key] = (ss, torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1])))
+        spatial_shapes, level_start_index = cache[key]
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
         # level_embed is handed over separately for the fused layers, which take the positional term as a constant and
         # return level_embed's gradient themselves; the stock layers ignore it and differentiate through `pos`
         memory = self.encoder(src_flatten, spatial_shapes, level_start_index, valid_ratios, lvl_pos_embed_flatten,
-                              mask_flatten if use_masks else None, level_embed=self.level_embed)
+                              mask_flatten if use_masks else None, level_embed=self.level_embed,
+                              spatial_shapes_list=shapes_list)
         return memory, spatial_shapes, level_start_index
 
 
