@@ -1,6 +1,6 @@
 """Quick GPU development check: parity at small shapes + timing at cfg3.  Not a test, not the bench."""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 import vision_instance_seg_b200 as pkg

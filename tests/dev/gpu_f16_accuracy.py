@@ -1,6 +1,6 @@
 """Per-level error of the fp16-accumulation mode vs the exact fp32 mode (cfg3 geometry, few images)."""
 import json, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 from vision_instance_seg_b200 import workloads as W, MultiScaleDeformableAttention as MSDA
