@@ -18,7 +18,32 @@ namespace msda_enc {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxBlocks = 148 * 8;          // persistent grids: at most 8 CTAs per SM of a B200
+constexpr int kMaxBlocks = 148 * 8;          // persistent grids: at most 8 CTAs per SM of a B200 (scratch sizing bound)
+
+// Persistent grids are sized to exactly one resident wave: (CTAs of this kernel that fit on an SM) x (SM count), capped by
+// `cap` — a grid of 4 CTAs/SM for a kernel that only fits 3 runs a second, one-third-full wave (measured: LayerNorm
+// backward 0.345 -> see DESIGN §3.5).  The two device queries are cached per kernel.
+struct OccupancyEntry { const void* fn; size_t smem; int per_sm; };
+
+template <typename K>
+static int resident_grid(K kernel, size_t dyn_smem, long long wanted, int cap) {
+  static thread_local OccupancyEntry cache[32];
+  static thread_local int cached = 0, sms = 0;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  int per_sm = 0;
+  for (int i = 0; i < cached; ++i)
+    if (cache[i].fn == key && cache[i].smem == dyn_smem) per_sm = cache[i].per_sm;
+  if (per_sm == 0) {
+    int dev = 0;
+    if (sms == 0 && (cudaGetDevice(&dev) != cudaSuccess ||
+                     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1))
+      sms = 148;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 2;
+    if (cached < 32) cache[cached++] = OccupancyEntry{key, dyn_smem, per_sm};
+  }
+  const long long g = std::min<long long>(std::min<long long>(wanted, static_cast<long long>(per_sm) * sms), cap);
+  return static_cast<int>(std::max<long long>(g, 1));
+}
 
 __device__ __forceinline__ float4 bf16x4_to_float4(const uint2& u) {
   return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
@@ -272,28 +297,26 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 template <int NV>
 static int launch_ln_fwd(const float* x, const void* delta16, const float* gamma, const float* beta, float* y, void* y16,
                          float* mean, float* rstd, long long rows, float eps, cudaStream_t st) {
-  const int grid = static_cast<int>(std::min<long long>((rows + kWarps - 1) / kWarps, kMaxBlocks));
+  const int grid = resident_grid(add_layernorm_fwd_kernel<NV>, 0, (rows + kWarps - 1) / kWarps, kMaxBlocks);
   add_layernorm_fwd_kernel<NV><<<grid, kThreads, 0, st>>>(x, static_cast<const __nv_bfloat16*>(delta16), gamma, beta, y,
                                                           static_cast<__nv_bfloat16*>(y16), mean, rstd, rows, eps);
   return static_cast<int>(cudaGetLastError());
 }
 
-static int ln_bwd_blocks(long long rows) {
-  return static_cast<int>(std::min<long long>((rows + kWarps - 1) / kWarps, 148 * 4));
-}
+constexpr int kMaxLnBwdBlocks = 148 * 4;     // scratch sizing bound of the dgamma / dbeta partials
 
 template <int NV>
 static int launch_ln_bwd(const float* gy, const void* gy16, const float* x, const void* delta16, const float* mean,
                          const float* rstd, const float* gamma, float* dx, void* ddelta16, float* dgamma, float* dbeta,
                          float* partials, long long rows, cudaStream_t st) {
   constexpr int C = NV * 128;
-  const int grid = ln_bwd_blocks(rows);
   const size_t smem = static_cast<size_t>(kWarps) * 2 * C * sizeof(float);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(add_layernorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
   }
+  const int grid = resident_grid(add_layernorm_bwd_kernel<NV>, smem, (rows + kWarps - 1) / kWarps, kMaxLnBwdBlocks);
   add_layernorm_bwd_kernel<NV><<<grid, kThreads, smem, st>>>(
       gy, static_cast<const __nv_bfloat16*>(gy16), x, static_cast<const __nv_bfloat16*>(delta16), mean, rstd, gamma, dx,
       static_cast<__nv_bfloat16*>(ddelta16), partials, rows);
@@ -318,10 +341,11 @@ static int launch_colsum(void* g16, const void* h16, float* out, float* partials
   const int TC = colsum_tile(C);
   const int RL = kThreads / TC;
   const int tiles = (C / 8 + TC - 1) / TC;
-  long long gx = (total + RL - 1) / RL;
-  gx = std::max<long long>(1, std::min<long long>(gx, kMaxBlocks / tiles > 0 ? kMaxBlocks / tiles : 1));
-  const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(tiles));
   const size_t smem = static_cast<size_t>(kThreads) * 8 * sizeof(float);
+  const int resident = resident_grid(colsum_kernel<RELU>, smem, 1ll << 40, kMaxBlocks);
+  long long gx = (total + RL - 1) / RL;
+  gx = std::max<long long>(1, std::min<long long>(gx, resident / tiles > 0 ? resident / tiles : 1));
+  const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(tiles));
   colsum_kernel<RELU><<<grid, kThreads, smem, st>>>(static_cast<__nv_bfloat16*>(g16), static_cast<const __nv_bfloat16*>(h16),
                                                    partials, total, span, row_begin, rows_per_batch, C, TC);
   cudaError_t e = cudaGetLastError();
@@ -339,7 +363,7 @@ extern "C" int msda_enc_add_cast(const float* a, const float* b, void* out16, si
   if (n == 0 || (n & 7) != 0) return MSDA_ERR_BAD_SHAPE;
   if (!aligned16(a) || !aligned16(b) || !aligned16(out16)) return MSDA_ERR_MISALIGNED;
   const size_t n8 = n / 8;
-  const int grid = static_cast<int>(std::min<size_t>((n8 + kThreads - 1) / kThreads, kMaxBlocks));
+  const int grid = resident_grid(add_cast_kernel, 0, static_cast<long long>((n8 + kThreads - 1) / kThreads), kMaxBlocks);
   add_cast_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), static_cast<uint4*>(out16), n8);
   return static_cast<int>(cudaGetLastError());
@@ -366,7 +390,7 @@ extern "C" int msda_enc_add_layernorm_forward(const float* x, const void* delta1
 
 extern "C" size_t msda_enc_add_layernorm_backward_scratch_bytes(int C) {
   if (C <= 0) return 0;
-  return static_cast<size_t>(148 * 4) * 2 * C * sizeof(float);
+  return static_cast<size_t>(kMaxLnBwdBlocks) * 2 * C * sizeof(float);
 }
 
 extern "C" int msda_enc_add_layernorm_backward(const float* gy, const void* gy16, const float* x, const void* delta16,
