@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the config's)")
     ap.add_argument("--layers", type=int, default=None)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=None, help="default: --steps")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
@@ -307,7 +307,7 @@ def run_b200(args):
         e2e = {"value": pts_per_step * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": args.e2e_steps,
                "api": "HostPipeline.submit (pinned host operands -> ms_deform_attn_forward/backward -> pinned host results; "
-                      "3 streams, double-buffered staging)"}
+                      "3 streams, batch cut into 4 pieces, triple-buffered staging)"}
         del host_in, host_out, pipe
 
     if rank != 0:
@@ -526,6 +526,8 @@ def _shutdown():
 
 def main():
     args = parse_args()
+    if args.e2e_steps is None:
+        args.e2e_steps = args.steps
     if args.impl == "reference":
         return run_reference(args)
     if args.gpus > 1 and "RANK" not in os.environ:

@@ -3,9 +3,12 @@
 `HostPipeline.submit()` enqueues, for one call of the path, the host→device copies of (value,
 sampling_locations, attention_weights, grad_output), `ms_deform_attn_forward` + `ms_deform_attn_backward`
 through the extension-level API, and the device→host copies of (output, grad_value, grad_sampling_loc,
-grad_attn_weight) — on three CUDA streams with double-buffered device staging, so that the H2D of call k+1, the
-kernels of call k and the D2H of call k-1 overlap (PCIe is full duplex).  Nothing is cached between calls: every
-submit moves all of its bytes.  This is the end-to-end entry point `bench.py` times as `e2e`.
+grad_attn_weight) — on three CUDA streams with multi-buffered device staging, so that the H2D of one piece, the kernels
+of the previous one and the D2H of the one before overlap (PCIe is full duplex).  Images are independent in this
+operator (output row (b, q) depends only on value[b], loc[b, q], attn[b, q]), so a call is cut along the batch into
+`chunks` pieces that flow through the pipeline one after the other: the fill / drain bubble is one piece, not one
+call, and the device staging is a fraction of the call's footprint.  Nothing is cached between calls: every submit
+moves all of its bytes.  This is the end-to-end entry point `bench.py` times as `e2e`.
 """
 from __future__ import annotations
 
@@ -16,12 +19,13 @@ from . import MultiScaleDeformableAttention as MSDA
 
 class HostPipeline:
     def __init__(self, spatial_shapes: torch.Tensor, level_start_index: torch.Tensor, device, im2col_step: int = 128,
-                 depth: int = 2):
+                 depth: int = 3, chunks: int = 4):
         self.device = torch.device(device)
         self.shapes = spatial_shapes.to(self.device, torch.int64).contiguous()
         self.lsi = level_start_index.to(self.device, torch.int64).contiguous()
         self.im2col_step = im2col_step
         self.depth = depth
+        self.chunks = max(1, int(chunks))
         self.s_in = torch.cuda.Stream(self.device)
         self.s_run = torch.cuda.Stream(self.device)
         self.s_out = torch.cuda.Stream(self.device)
@@ -36,6 +40,16 @@ class HostPipeline:
     def submit(self, host_in, host_out):
         """host_in = (value, sampling_locations, attention_weights, grad_output) pinned CPU tensors;
         host_out = (output, grad_value, grad_sampling_loc, grad_attn_weight) pinned CPU tensors to fill."""
+        n = host_in[0].shape[0]
+        pieces = min(self.chunks, n)
+        base, rem = divmod(n, pieces)
+        start = 0
+        for i in range(pieces):
+            stop = start + base + (1 if i < rem else 0)
+            self._submit_piece([h[start:stop] for h in host_in], [h[start:stop] for h in host_out])
+            start = stop
+
+    def _submit_piece(self, host_in, host_out):
         k = self.count % self.depth
         first_use = self.count < self.depth
         self.count += 1
