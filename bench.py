@@ -508,6 +508,7 @@ def run_train_step(args):
                    "optimizer": "AdamW(fused)", "autocast": "bf16",
                    "parallelism": f"dp{world}", "grad_allreduce_bytes": int(buckets.flat.numel() * 4) if world > 1 else 0,
                    "grad_buckets": len(buckets.slices), "points_per_step": pts_per_step, "final_loss": final_loss,
+                   "peak_device_memory_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2),
                    "l2_policy": "activations of one step (GBs) >> 126 MB L2; no flush needed"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
     }
