@@ -276,10 +276,34 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
 
+  // one sampling point: four unconditional 16-byte corner loads + the weighted accumulation
+  auto sample = [&](float x, float y, float a, int H, int W, float Hf, float Wf, const char* vl) {
+    const Taps t = make_taps(x, y, H, W, Hf, Wf);
+    // pixel index * pixel stride fits 32 bits (validated on the host): one IMAD.WIDE per corner
+    const uint4 u00 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i00) * pix_bytes));
+    const uint4 u01 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i01) * pix_bytes));
+    const uint4 u10 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i10) * pix_bytes));
+    const uint4 u11 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i11) * pix_bytes));
+    const float ah = t.hhm * a, al = t.lhm * a;
+    axpy16<T>(acc, u00, make_weight<T>(ah * t.hwm));
+    axpy16<T>(acc, u01, make_weight<T>(ah * t.lwm));
+    axpy16<T>(acc, u10, make_weight<T>(al * t.hwm));
+    axpy16<T>(acc, u11, make_weight<T>(al * t.lwm));
+  };
   for (int l = 0; l < L; ++l) {
     const int H = meta.H[l], W = meta.W[l];
     const float Hf = static_cast<float>(H), Wf = static_cast<float>(W);
     const char* vl = vb + static_cast<size_t>(meta.start[l]) * pix_bytes;
+    if ((P & 1) == 0) {
+      // the shared-memory pipe is the one the gathers saturate: fetch two points' (x, y) / weights per LDS
+      for (int p = 0; p < P; p += 2) {
+        const float4 xy2 = *reinterpret_cast<const float4*>(myloc + 2 * (l * P + p));
+        const float2 a2 = *reinterpret_cast<const float2*>(myattn + l * P + p);
+        sample(xy2.x, xy2.y, a2.x, H, W, Hf, Wf, vl);
+        sample(xy2.z, xy2.w, a2.y, H, W, Hf, Wf, vl);
+      }
+      continue;
+    }
 #pragma unroll 2
     for (int p = 0; p < P; ++p) {
       const float2 xy = *reinterpret_cast<const float2*>(myloc + 2 * (l * P + p));
