@@ -73,6 +73,8 @@ if __name__ == "__main__":
     if "--fused-only" in sys.argv:
         c3 = W.CONFIGS["cfg3_swinl_1024_bf16"]["shapes"]
         timing("cfg3", W.make_encoder_inputs, torch.bfloat16, shapes=c3, batch=16)
+        timing("cfg3_fp32", W.make_encoder_inputs, torch.float32, shapes=c3, batch=16)
+        timing("cfg3_uniform", W.make_uniform_inputs, torch.bfloat16, shapes=c3, batch=16)
         timing_fused("cfg3_fused", torch.bfloat16, c3, 16)
         timing_fused("cfg3_fused_fp32", torch.float32, c3, 16)
         timing("cfg4_dec", W.make_decoder_inputs, torch.bfloat16, shapes=c3, batch=16)
