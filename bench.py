@@ -327,7 +327,10 @@ def run_b200(args):
                                 "frac": ab["fwd"] / (fwd_avg * 1e-3) / 1e9 / peak if fwd_avg else None,
                                 "algorithmic_bytes_per_launch": ab["fwd"], "avg_launch_ms": fwd_avg,
                                 "traffic": ncu_traffic_bytes("forward")},
-                    "step_frac": (ab["fwd"] + ab["bwd"]) * layers / (ms_per_step * 1e-3) / 1e9 / peak}
+                    "step_frac": (ab["fwd"] + ab["bwd"]) * layers / (ms_per_step * 1e-3) / 1e9 / peak,
+                    # sampled points/s of the forward and the backward kernel on their own
+                    "forward_points_per_s": ab["points"] / (fwd_avg * 1e-3) if fwd_avg else None,
+                    "backward_points_per_s": ab["points"] / (bwd_avg * 1e-3)}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
