@@ -330,7 +330,13 @@ def run_b200(args):
                     "step_frac": (ab["fwd"] + ab["bwd"]) * layers / (ms_per_step * 1e-3) / 1e9 / peak,
                     # sampled points/s of the forward and the backward kernel on their own
                     "forward_points_per_s": ab["points"] / (fwd_avg * 1e-3) if fwd_avg else None,
-                    "backward_points_per_s": ab["points"] / (bwd_avg * 1e-3)}
+                    "backward_points_per_s": ab["points"] / (bwd_avg * 1e-3),
+                    # what actually binds the backward: 4 corner-row reductions per sampled point
+                    # against the measured L2 reduction ceiling for 64-byte packed-fp16 rows (profiles/microbench_r01.jsonl)
+                    "binding_resource": {"name": "L2 reduction path (red.global.add.noftz.v4.f16x2, 64-byte rows)",
+                                         "achieved_Grows_per_s": 4 * ab["points"] / (bwd_avg * 1e-3) / 1e9,
+                                         "measured_ceiling_Grows_per_s": 85.0,
+                                         "frac": 4 * ab["points"] / (bwd_avg * 1e-3) / 85.0e9} if dtype != torch.float32 else None}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
