@@ -169,7 +169,34 @@ def test_config3_encoder_shape_bf16_one_image(ops):
     got = run_cuda(ops, value, ss_, lsi_, loc_, attn_, go_, torch.bfloat16)
     want = ms_deform_attn_oracle_grads(value.to(torch.bfloat16).float(), ss_, loc_, attn_, go_.to(torch.bfloat16).float(),
                                        dtype=torch.float32)
+    # grad_loc is compared away from integer pixel lines (see test_config5_encoder_shape_bf16_one_image)
+    wh = torch.stack([ss_[:, 1], ss_[:, 0]], -1).to(torch.float32)[None, None, None, :, None, :]
+    px = loc_ * wh - 0.5
+    smooth = ((px - px.round()).abs() > 1e-3).all(-1, keepdim=True).expand_as(loc_)
     for name, a, b in zip(("out", "grad_value", "grad_loc", "grad_attn"), got, want):
+        a, b = a.detach().float().cpu(), b.float()
+        if name == "grad_loc":
+            a, b = a * smooth, b * smooth
+        assert rel_to_max(a, b) < 2e-2, name
+
+
+def test_config5_encoder_shape_bf16_one_image(ops):
+    """configs[4] geometry (2048^2 -> 256/128/64/32, 87 040 queries) at batch 1 against the oracle (fp32 on the CPU)."""
+    from vision_instance_seg_b200 import workloads as W
+    cfg = W.CONFIGS["cfg5_2048_bf16"]
+    v, ss, lsi, loc, attn = W.make_encoder_inputs(cfg["shapes"], 1, torch.bfloat16, device="cpu", seed=77)
+    go = torch.randn(1, loc.shape[1], 256, generator=torch.Generator().manual_seed(8))
+    got = run_cuda(ops, v.float(), ss, lsi, loc, attn, go, torch.bfloat16)
+    want = ms_deform_attn_oracle_grads(v.float(), ss, loc, attn, go.to(torch.bfloat16).float(), dtype=torch.float32)
+    # 11 M sampling points: a handful sit within float rounding of an integer pixel line, where the bilinear derivative
+    # jumps and the fp32 oracle and the kernel may legitimately pick different cells; grad_loc is compared away from them
+    wh = torch.stack([ss[:, 1], ss[:, 0]], -1).to(torch.float32)[None, None, None, :, None, :]
+    px = loc * wh - 0.5
+    smooth = ((px - px.round()).abs() > 1e-3).all(-1, keepdim=True).expand_as(loc)
+    for name, a, b in zip(("out", "grad_value", "grad_loc", "grad_attn"), got, want):
+        a, b = a.detach().float().cpu(), b.float()
+        if name == "grad_loc":
+            a, b = a * smooth, b * smooth
         assert rel_to_max(a, b) < 2e-2, name
 
 
