@@ -139,3 +139,47 @@ def test_module_matches_independent_module_golden(ops, fused, dtype):
         assert rel_to_max(q.grad, g["grad_query"]) < tol and rel_to_max(s.grad, g["grad_src"]) < tol, name
         for k, p in m.named_parameters():
             assert rel_to_max(p.grad, g["grad." + k]) < tol, (name, k)
+
+
+def test_unmodified_upstream_autograd_function_runs_on_the_installed_extension(ops):
+    """The body of upstream's ops/functions/ms_deform_attn_func.py::MSDeformAttnFunction, restated with its own call
+    pattern (`import MultiScaleDeformableAttention as MSDA`, positional arguments, three returned gradients), runs
+    unchanged once `install_as_upstream_extension()` has been called, and matches the oracle."""
+    import sys
+    from torch.autograd import Function
+    from torch.autograd.function import once_differentiable
+    from oracle import ms_deform_attn_oracle_grads
+    from tests.helpers import random_problem
+    ops.install_as_upstream_extension()
+    try:
+        import MultiScaleDeformableAttention as MSDA
+
+        class UpstreamStyleFunction(Function):
+            @staticmethod
+            def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights, im2col_step):
+                ctx.im2col_step = im2col_step
+                output = MSDA.ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                                                     attention_weights, ctx.im2col_step)
+                ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights)
+                return output
+
+            @staticmethod
+            @once_differentiable
+            def backward(ctx, grad_output):
+                value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights = ctx.saved_tensors
+                grad_value, grad_sampling_loc, grad_attn_weight = MSDA.ms_deform_attn_backward(
+                    value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights, grad_output,
+                    ctx.im2col_step)
+                return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
+
+        value, ss, lsi, loc, attn, go = random_problem(2, 8, 32, 23, [(9, 7), (4, 5)], 4, seed=31, dtype=torch.float32)
+        v = value.cuda().requires_grad_(True)
+        lo = loc.cuda().requires_grad_(True)
+        at = attn.cuda().requires_grad_(True)
+        out = UpstreamStyleFunction.apply(v, ss.cuda(), lsi.cuda(), lo, at, 64)
+        out.backward(go.cuda())          # upstream passes grad_output as autograd hands it over (contiguous here)
+        want = ms_deform_attn_oracle_grads(value.double(), ss, loc.double(), attn.double(), go.double())
+        for a, b in zip((out, v.grad, lo.grad, at.grad), want):
+            assert rel_to_max(a, b) < 1e-5
+    finally:
+        sys.modules.pop("MultiScaleDeformableAttention", None)

@@ -150,3 +150,24 @@ def test_synthetic_workloads_on_cpu():
     assert torch.allclose(attn.sum((-1, -2)), torch.ones(2, 80, 2), atol=1e-5)
     v, ss, lsi, loc, attn = W.make_decoder_inputs([(8, 8), (4, 4)], 2, torch.bfloat16, queries=5, n_heads=2, head_dim=8, device="cpu")
     assert v.dtype == torch.bfloat16 and loc.dtype == torch.float32 and tuple(loc.shape) == (2, 5, 2, 2, 4, 2)
+
+
+def test_install_as_upstream_extension_binds_the_upstream_import_name(monkeypatch):
+    """Upstream's ms_deform_attn_func.py does `import MultiScaleDeformableAttention as MSDA`; after the helper that import
+    resolves to this package's stand-in (same two functions), so an unmodified checkout needs no extension build."""
+    import importlib
+    import sys
+    monkeypatch.delitem(sys.modules, "MultiScaleDeformableAttention", raising=False)
+    with pytest.raises(ImportError):
+        importlib.import_module("MultiScaleDeformableAttention")
+    mod = pkg.install_as_upstream_extension()
+    try:
+        import MultiScaleDeformableAttention as MSDA
+        assert MSDA is mod is pkg.MultiScaleDeformableAttention
+        assert callable(MSDA.ms_deform_attn_forward) and callable(MSDA.ms_deform_attn_backward)
+        # the upstream autograd function body, verbatim in spirit: it only needs these two entry points
+        with pytest.raises(RuntimeError):          # CPU tensors: same error class as upstream's AT_ERROR
+            MSDA.ms_deform_attn_forward(torch.zeros(1, 4, 1, 8), torch.tensor([[2, 2]]), torch.tensor([0]),
+                                        torch.zeros(1, 1, 1, 1, 1, 2), torch.zeros(1, 1, 1, 1, 1), 64)
+    finally:
+        sys.modules.pop("MultiScaleDeformableAttention", None)

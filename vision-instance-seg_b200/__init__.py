@@ -21,5 +21,24 @@ from ._lib import library_path, load_library  # noqa: F401
 from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction  # noqa: F401
 from .modules import MSDeformAttn, set_fused_encoder_layers, set_fused_preop  # noqa: F401
 
+
+
+def install_as_upstream_extension(name: str = "MultiScaleDeformableAttention"):
+    """Register this package's stand-in under the import name of upstream's compiled extension, so that an unmodified
+    MaskDINO / Mask2Former / Deformable-DETR checkout — whose ``ops/functions/ms_deform_attn_func.py`` does
+    ``import MultiScaleDeformableAttention as MSDA`` — binds to the B200 kernels without building its own extension.
+
+    Call it before the first import of the upstream package, e.g. in the reference's training scripts right before
+    ``from maskdino import add_maskdino_config`` (/root/reference/training/maskdino/train_full.py:28)::
+
+        import vision_instance_seg_b200 as b200
+        b200.install_as_upstream_extension()
+
+    Returns the module that is now importable as ``name``.  An already imported module of that name is replaced."""
+    import sys
+    sys.modules[name] = MultiScaleDeformableAttention
+    return MultiScaleDeformableAttention
+
+
 __all__ = ["MSDeformAttn", "MSDeformAttnFunction", "MSDeformAttnFusedFunction", "MultiScaleDeformableAttention",
-           "set_fused_preop", "set_fused_encoder_layers", "load_library", "library_path"]
+           "set_fused_preop", "set_fused_encoder_layers", "install_as_upstream_extension", "load_library", "library_path"]
