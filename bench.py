@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
     ap.add_argument("--fused-preop", action="store_true",
                     help="train-step workloads: fold softmax + sampling-location arithmetic into the kernels")
+    ap.add_argument("--forward-only", action="store_true",
+                    help="train-step workloads: time the encoder forward alone under no_grad (inference, reference call stack "
+                         "evaluate.py / visualize.py); the metric counts forward sampled points only")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="train-step workloads: capture forward + backward + all-reduce + optimizer in one CUDA graph")
     ap.add_argument("--fused-layers", action="store_true",
@@ -405,6 +408,10 @@ def run_train_step(args):
     loss_host = torch.zeros(1).pin_memory()
 
     def step_body(x):
+        if args.forward_only:
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=not args.fused_layers):
+                memory, _, _ = enc(x, None, pos)
+            return memory.float().square().mean()
         buckets.zero()
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=not args.fused_layers):
             memory, _, _ = enc(x, None, pos)       # the fused layers are bf16 by construction
@@ -497,6 +504,12 @@ def run_train_step(args):
     if args.fused_preop:        # sampling locations / attention weights never reach HBM: raw offsets + logits instead (same sizes)
         pass
     roofline = None
+    if fwd_ms and not bwd_ms:
+        fwd_avg = statistics.mean(fwd_ms)
+        roofline = {"bound": "hbm", "kernel": "msda_fwd (forward gather)", "achieved": ab["fwd"] / (fwd_avg * 1e-3) / 1e9,
+                    "peak": peak, "unit": "GB/s", "frac": ab["fwd"] / (fwd_avg * 1e-3) / 1e9 / peak, "traffic": None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["fwd"], "avg_launch_ms": fwd_avg,
+                    "launches_timed": len(fwd_ms), "msda_share_of_step": sum(fwd_ms) / args.steps / ms_per_step}
     if bwd_ms:
         bwd_avg, fwd_avg = statistics.mean(bwd_ms), statistics.mean(fwd_ms)
         roofline = {"bound": "hbm", "kernel": "msda_bwd (backward gather + grad_value scatter)",
@@ -513,7 +526,7 @@ def run_train_step(args):
         "config": {"workload": args.workload, "global_batch": global_batch, "per_gpu_batch": count, "layers": layers,
                    "levels": shapes, "queries": S, "heads": M, "head_dim": C // M, "points": P, "d_ffn": cfg["d_ffn"],
                    "fused_preop": bool(args.fused_preop or args.fused_layers), "fused_layers": bool(args.fused_layers),
-                   "cuda_graph": bool(args.cuda_graph),
+                   "cuda_graph": bool(args.cuda_graph), "forward_only": bool(args.forward_only),
                    "optimizer": "AdamW(fused)", "autocast": "bf16",
                    "parallelism": f"dp{world}", "grad_allreduce_bytes": int(buckets.flat.numel() * 4) if world > 1 else 0,
                    "grad_buckets": len(buckets.slices), "points_per_step": pts_per_step, "final_loss": final_loss,
