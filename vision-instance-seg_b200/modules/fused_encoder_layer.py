@@ -32,6 +32,17 @@ from .. import encoder_ops as ops
 _BF16 = torch.bfloat16
 
 
+def _linear_relu(bias16: torch.Tensor, x16: torch.Tensor, w16_t: torch.Tensor) -> torch.Tensor:
+    """relu(x @ w^T + b) with the bias + ReLU in the GEMM epilogue (cuBLASLt) where this torch build exposes it."""
+    fused = getattr(torch, "_addmm_activation", None)
+    if fused is not None:
+        try:
+            return fused(bias16, x16, w16_t, use_gelu=False)
+        except (TypeError, RuntimeError):
+            pass
+    return torch.relu_(torch.addmm(bias16, x16, w16_t))
+
+
 def _mm_f32(a16: torch.Tensor, b16: torch.Tensor) -> torch.Tensor:
     """bf16 x bf16 -> fp32 GEMM (weight gradients): fp32 output straight from the accumulator where torch offers it."""
     try:
@@ -66,7 +77,7 @@ class FusedEncoderLayerFunction(Function):
                                                  off.view(N, S, M, L, P, 2), lg.view(N, S, M, L * P), step).view(T, C)
         o = torch.addmm(o_b16, attn, o_w16.t())
         x1, x1_16, mean1, rstd1 = ops.add_layernorm_forward(src2d, o, n1_w, n1_b, cfg["eps1"])
-        h = torch._addmm_activation(l1_b16, x1_16, l1_w16.t(), use_gelu=False)
+        h = _linear_relu(l1_b16, x1_16, l1_w16.t())
         f = torch.addmm(l2_b16, h, l2_w16.t())
         x2, x2_16, mean2, rstd2 = ops.add_layernorm_forward(x1, f, n2_w, n2_b, cfg["eps2"], want16=cfg["want16"])
         ctx.cfg = cfg
