@@ -171,3 +171,16 @@ def test_install_as_upstream_extension_binds_the_upstream_import_name(monkeypatc
                                         torch.zeros(1, 1, 1, 1, 1, 2), torch.zeros(1, 1, 1, 1, 1), 64)
     finally:
         sys.modules.pop("MultiScaleDeformableAttention", None)
+
+
+def test_decoder_reference_points_input():
+    g = torch.Generator().manual_seed(0)
+    boxes = torch.rand(2, 5, 4, generator=g)
+    vr = torch.tensor([[[1.0, 1.0], [0.5, 0.75], [0.25, 1.0]], [[0.8, 0.9], [1.0, 1.0], [0.6, 0.7]]])
+    out = W.decoder_reference_points_input(boxes, vr)
+    assert out.shape == (2, 5, 3, 4)
+    assert torch.allclose(out[1, 3, 2], boxes[1, 3] * torch.tensor([0.6, 0.7, 0.6, 0.7]))
+    pts = W.decoder_reference_points_input(boxes[..., :2], vr)
+    assert pts.shape == (2, 5, 3, 2) and torch.allclose(pts[0, 0, 1], boxes[0, 0, :2] * torch.tensor([0.5, 0.75]))
+    with pytest.raises(ValueError):
+        W.decoder_reference_points_input(torch.rand(1, 2, 3), vr[:1])

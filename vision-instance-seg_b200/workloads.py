@@ -59,6 +59,20 @@ def get_reference_points(spatial_shapes: torch.Tensor, valid_ratios: torch.Tenso
     return reference_points[:, :, None] * valid_ratios[:, None]
 
 
+def decoder_reference_points_input(reference_points: torch.Tensor, valid_ratios: torch.Tensor) -> torch.Tensor:
+    """What the deformable decoder hands to its cross-attention ``MSDeformAttn`` as ``reference_points`` (upstream
+    ``TransformerDecoder.forward`` in maskdino/modeling/transformer_decoder/dino_decoder.py, from Deformable-DETR):
+    per-level copies of the (sigmoid) query boxes / points, scaled by each level's valid ratio.
+
+    reference_points: (N, nq, 4) boxes (cx, cy, w, h) or (N, nq, 2) points in [0, 1]; valid_ratios: (N, L, 2) (w, h).
+    Returns (N, nq, L, 4) or (N, nq, L, 2)."""
+    if reference_points.shape[-1] == 4:
+        return reference_points[:, :, None] * torch.cat([valid_ratios, valid_ratios], -1)[:, None]
+    if reference_points.shape[-1] == 2:
+        return reference_points[:, :, None] * valid_ratios[:, None]
+    raise ValueError("reference_points must end in 2 or 4 coordinates")
+
+
 def init_offset_pattern(n_heads: int, n_levels: int, n_points: int) -> torch.Tensor:
     """(M, L, P, 2) the sampling-offset bias MSDeformAttn._reset_parameters installs."""
     thetas = torch.arange(n_heads, dtype=torch.float32) * (2.0 * math.pi / n_heads)
