@@ -29,7 +29,7 @@ def _draw(seed):
                 L=L, P=rng.randint(1, 5), shapes=shapes, seed=seed)
 
 
-@pytest.mark.parametrize("seed", list(range(16)))
+@pytest.mark.parametrize("seed", list(range(16)) + [1001, 1016])      # 1001 (L*P = 2), 1016 (L*P = 3, one pair per warp): found by tests/dev/fuzz_many.py
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_random_shapes_plain_operator(ops, seed, dtype):
     c = _draw(seed)

@@ -37,6 +37,12 @@ namespace msda {
 // are plain coalesced 128-bit transfers; each pair's row gets 16 bytes of padding so that the G-lane groups
 // of a warp read their rows from distinct banks.
 // =====================================================================================================
+// Row strides of the staged rows, in floats: the payload rounded up to a multiple of 4 plus 4 floats of padding, so that
+// every row (and every warp's block of rows) starts 16-byte aligned for any L*P — float2 / float4 reads of a row are
+// then always legal — and the G-lane groups of a warp still read their rows from distinct banks.
+__host__ __device__ inline int loc_row_stride(int LP) { return ((2 * LP + 3) & ~3) + 4; }
+__host__ __device__ inline int attn_row_stride(int LP) { return ((LP + 3) & ~3) + 4; }
+
 struct WarpStage {
   float* loc;        // [GPW][2*LP + 4]
   float* attn;       // [GPW][LP + 4]
@@ -240,8 +246,8 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / G, c = lane % G;
   WarpStage ws;
-  ws.loc_stride = 2 * LP + 4;
-  ws.attn_stride = LP + 4;
+  ws.loc_stride = loc_row_stride(LP);
+  ws.attn_stride = attn_row_stride(LP);
   ws.loc = smem + warp * GPW * (ws.loc_stride + ws.attn_stride);
   ws.attn = ws.loc + GPW * ws.loc_stride;
   ws.gattn = nullptr;
@@ -294,7 +300,7 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
     const int H = meta.H[l], W = meta.W[l];
     const float Hf = static_cast<float>(H), Wf = static_cast<float>(W);
     const char* vl = vb + static_cast<size_t>(meta.start[l]) * pix_bytes;
-    if ((P & 1) == 0) {
+    if ((P & 1) == 0) {                    // rows are 16-byte aligned (loc_row_stride); l*P + p is even here
       // the shared-memory pipe is the one the gathers saturate: fetch two points' (x, y) / weights per LDS
       for (int p = 0; p < P; p += 2) {
         const float4 xy2 = *reinterpret_cast<const float4*>(myloc + 2 * (l * P + p));
@@ -393,8 +399,8 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / G, c = lane % G;
   WarpStage ws;
-  ws.loc_stride = 2 * LP + 4;
-  ws.attn_stride = LP + 4;
+  ws.loc_stride = loc_row_stride(LP);
+  ws.attn_stride = attn_row_stride(LP);
   ws.loc = smem + warp * GPW * (ws.loc_stride + (FUSED ? 2 : 1) * ws.attn_stride);
   ws.attn = ws.loc + GPW * ws.loc_stride;
   ws.gattn = FUSED ? ws.attn + GPW * ws.attn_stride : nullptr;
@@ -872,7 +878,9 @@ static size_t vec_smem_bytes(int L, int P, bool fused = false, bool bwd = false)
   constexpr int G = D / (16 / static_cast<int>(sizeof(T)));
   constexpr int GPW = 32 / G;
   const bool fb = fused && bwd;
-  return static_cast<size_t>(kWarps) * GPW * ((fb ? 4 : 3) * L * P + (fb ? 12 : 8) + (fused ? 4 * L : 0)) * sizeof(float);
+  const int LP = L * P;
+  return static_cast<size_t>(kWarps) * GPW * (loc_row_stride(LP) + (fb ? 2 : 1) * attn_row_stride(LP) + (fused ? 4 * L : 0)) *
+         sizeof(float);
 }
 
 template <typename K>
