@@ -230,3 +230,11 @@ def test_module_fused_flag_matches_unfused(ops, ref_dim):
     r = ref.clone().requires_grad_(True)
     m(query, r, src, ss, lsi).sum().backward()
     assert r.grad is not None and torch.isfinite(r.grad).all()
+
+
+def test_fused_backward_at_the_48KB_shared_memory_boundary(ops):
+    """D = 16 in bf16 puts 16 pairs in a warp; with L*P = 15 the fused backward needs exactly 48 KB of dynamic shared
+    memory next to the kernel's static level table — the opt-in for > 48 KB must already be taken there (found by
+    tests/dev/fuzz_more.py)."""
+    check_fused(ops, fused_problem(2, 3, 16, 48, [(14, 2), (8, 13), (5, 1), (1, 3), (11, 10)], 3, 2, seed=6), torch.bfloat16)
+    check_fused(ops, fused_problem(2, 3, 16, 48, [(14, 2), (8, 13), (5, 1), (1, 3), (11, 10)], 3, 4, seed=7), torch.float16)

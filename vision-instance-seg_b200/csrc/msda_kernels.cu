@@ -885,7 +885,8 @@ static size_t vec_smem_bytes(int L, int P, bool fused = false, bool bwd = false)
 
 template <typename K>
 static cudaError_t allow_smem(K kernel, size_t bytes) {
-  if (bytes <= 48 * 1024) return cudaSuccess;
+  // the kernels also hold a static LevelMeta (< 1 KB): opt in as soon as dynamic + static could pass the 48 KB default
+  if (bytes + 1024 <= 48 * 1024) return cudaSuccess;
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
 }
 
