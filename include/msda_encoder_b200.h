@@ -17,7 +17,7 @@
  * in one pass over HBM.  Conventions as in msda_b200.h: plain pointers, caller-owned buffers (16-byte aligned,
  * contiguous), work enqueued on `stream`, 0 / negative MSDA_ERR_* / positive cudaError_t returned, no allocation, no sync.
  * The 16-bit type is bfloat16 throughout (the autocast dtype of the path).  C must be a multiple of 128, at most 1024,
- * for the LayerNorm kernels; a multiple of 8 for the column sums.
+ * for the LayerNorm kernels; any C for the column sums (vector path when C is a multiple of 8).
  */
 #ifndef MSDA_ENCODER_B200_H_
 #define MSDA_ENCODER_B200_H_

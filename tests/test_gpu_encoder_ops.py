@@ -58,7 +58,7 @@ def test_add_layernorm_forward_backward(eops, C, rows):
     assert dd2 is None and rel_to_max(dx2, w2[3]) < 1e-5 and rel_to_max(dg2, w2[4]) < 2e-5 and rel_to_max(db2, w2[5]) < 2e-5
 
 
-@pytest.mark.parametrize("C", [8, 48, 128, 256, 384, 2048])
+@pytest.mark.parametrize("C", [2, 5, 8, 36, 48, 128, 256, 384, 2048])
 def test_colsum_and_segments(eops, C):
     g = torch.Generator().manual_seed(C)
     t = torch.randn(3, 301, C, generator=g).to(torch.bfloat16)
@@ -69,7 +69,7 @@ def test_colsum_and_segments(eops, C):
     assert rel_to_max(eops.colsum(big.cuda()), colsum_oracle(big)) < 1e-5
 
 
-@pytest.mark.parametrize("C", [256, 2048])
+@pytest.mark.parametrize("C", [3, 36, 256, 2048])
 def test_relu_bwd_colsum(eops, C):
     g = torch.Generator().manual_seed(C + 1)
     h = torch.relu(torch.randn(1237, C, generator=g)).to(torch.bfloat16)
@@ -85,8 +85,6 @@ def test_shape_validation(eops):
     x = torch.randn(4, 200, device="cuda")
     with pytest.raises(RuntimeError):
         eops.add_layernorm_forward(x, None, torch.ones(200, device="cuda"), torch.zeros(200, device="cuda"), 1e-5)
-    with pytest.raises(RuntimeError):
-        eops.colsum(torch.randn(4, 20, device="cuda").to(torch.bfloat16))
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -292,6 +292,37 @@ colsum_kernel(__nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ h
   }
 }
 
+// Any column count (rows not 16-byte aligned): scalar bf16 accesses, 8 row lanes x 32 columns per CTA.  Only the bias
+// gradients of very small sampling_offsets / attention_weights Linears (heads * levels * points not a multiple of 8) land here.
+template <bool RELU>
+__global__ void __launch_bounds__(kThreads)
+colsum_scalar_kernel(__nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ h, float* __restrict__ partials,
+                     long long total_rows, long long span, long long row_begin, long long rows_per_batch, int C) {
+  __shared__ float red[kWarps][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = blockIdx.y * 32 + cl;
+  float acc = 0.f;
+  if (col < C) {
+    for (long long r = static_cast<long long>(blockIdx.x) * kWarps + rl; r < total_rows; r += static_cast<long long>(gridDim.x) * kWarps) {
+      const long long n = r / span;
+      const long long row = n * rows_per_batch + row_begin + (r - n * span);
+      float v = __bfloat162float(g[row * C + col]);
+      if constexpr (RELU) {
+        if (!(__bfloat162float(h[row * C + col]) > 0.f)) { v = 0.f; g[row * C + col] = __float2bfloat16_rn(0.f); }
+      }
+      acc += v;
+    }
+  }
+  red[rl][cl] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32 && col < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
+    partials[static_cast<size_t>(blockIdx.x) * C + col] = s;
+  }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <int NV>
@@ -338,6 +369,17 @@ static int launch_colsum(void* g16, const void* h16, float* out, float* partials
                          long long row_begin, long long row_end, int C, cudaStream_t st) {
   const long long span = row_end - row_begin;
   const long long total = batch * span;
+  if (C % 8 != 0) {
+    const int tiles = (C + 31) / 32;
+    const int resident = resident_grid(colsum_scalar_kernel<RELU>, 0, 1ll << 40, kMaxBlocks);
+    long long gx = std::max<long long>(1, std::min<long long>((total + kWarps - 1) / kWarps, resident / tiles > 0 ? resident / tiles : 1));
+    colsum_scalar_kernel<RELU><<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(tiles)), kThreads, 0, st>>>(
+        static_cast<__nv_bfloat16*>(g16), static_cast<const __nv_bfloat16*>(h16), partials, total, span, row_begin, rows_per_batch, C);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+    finalize_partials_kernel<<<(C + 31) / 32, kThreads, 0, st>>>(partials, static_cast<int>(gx), C, out, out, C);
+    return static_cast<int>(cudaGetLastError());
+  }
   const int TC = colsum_tile(C);
   const int RL = kThreads / TC;
   const int tiles = (C / 8 + TC - 1) / TC;
@@ -426,10 +468,11 @@ static int colsum_common(bool relu, void* g16, const void* h16, float* out, void
                          long long batch, long long rows_per_batch, long long row_begin, long long row_end, int C, void* stream) {
   if (!g16 || !out || !scratch || (relu && !h16)) return MSDA_ERR_NULL_POINTER;
   if (batch <= 0 || rows_per_batch <= 0 || row_begin < 0 || row_end > rows_per_batch || row_end <= row_begin || C <= 0 ||
-      C % 8 != 0)
+      C > (1 << 20))
     return MSDA_ERR_BAD_SHAPE;
   if (scratch_bytes < msda_enc_colsum_scratch_bytes(C)) return MSDA_ERR_SCRATCH_TOO_SMALL;
-  if (!aligned16(g16) || !aligned16(h16) || !aligned16(scratch)) return MSDA_ERR_MISALIGNED;
+  if (C % 8 == 0 && (!aligned16(g16) || !aligned16(h16))) return MSDA_ERR_MISALIGNED;
+  if (!aligned16(scratch)) return MSDA_ERR_MISALIGNED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (relu)
     return launch_colsum<true>(g16, h16, out, static_cast<float*>(scratch), batch, rows_per_batch, row_begin, row_end, C, st);
