@@ -49,7 +49,8 @@ enum {
   MSDA_ERR_MISALIGNED = -4,      /* a buffer is not 16-byte aligned */
   MSDA_ERR_IM2COL_STEP = -5,     /* N % min(N, im2col_step) != 0 (upstream assert kept) */
   MSDA_ERR_SCRATCH_TOO_SMALL = -6,
-  MSDA_ERR_FUSED_UNSUPPORTED = -7 /* fused pre-op: head dim not in {16,32,64,128}, float64 values, or ref_dim not 2/4 */
+  MSDA_ERR_FUSED_UNSUPPORTED = -7, /* fused pre-op: head dim not in {16,32,64,128}, float64 values, or ref_dim not 2/4 */
+  MSDA_ERR_BAD_STRIDE = -8        /* *_strided entry points: stride < M*D, not a multiple of 16 bytes, or a path without stride support */
 };
 
 /* backward flags */
@@ -66,7 +67,13 @@ enum {
    *            same as fp32 accumulation followed by bf16 rounding. */
   MSDA_BWD_DEFAULT = 0,
   /* 16-bit values: accumulate in an fp32 scratch with red.global.add.v4.f32 instead (2x the reduction bytes). */
-  MSDA_BWD_GRAD_VALUE_FP32_ACCUM = 2
+  MSDA_BWD_GRAD_VALUE_FP32_ACCUM = 2,
+  /* Default mode, sparse levels.  A level with 2*Lq*P <= H_l*W_l (decoder cross-attention: a few hundred queries
+   * against 10^4 pixels; expected adds per element well below one) owns no accumulator rows: its contributions are
+   * added, unscaled, with packed 16-bit reductions in the value dtype straight into the zeroed grad_value rows, so the
+   * dense zero / sum / round passes over the accumulator (most of a decoder layer's backward) are paid for the coarse
+   * levels only.  This flag switches that off (every level goes through the fp16 buckets). */
+  MSDA_BWD_NO_SPARSE_DIRECT = 4
 };
 #define MSDA_BWD_ACCUM_DEPTH(depth) (((depth) & 0xffff) << 8)
 
@@ -106,6 +113,32 @@ int msda_backward(const void* value, const int64_t* spatial_shapes, const int64_
                   void* scratch, size_t scratch_bytes,
                   int N, int S, int M, int D, int Lq, int L, int P,
                   int value_dtype, int im2col_step, int flags, void* stream);
+
+/*
+ * Strided variants (decoder `value_proj` reuse).  The nine decoder layers of MaskDINO each run
+ * their own `value_proj` Linear over the same encoder memory; one GEMM with the nine weights stacked produces
+ * (N, S, layers, M*D), in which layer i's `value` is the view [:, :, i] -- dense per pixel row, but with
+ * `value_pixel_stride = layers*M*D` elements between neighbouring pixels (and S*value_pixel_stride between images).
+ * These entry points read such a view in place and write `grad_value` into the matching view of one shared
+ * (N, S, layers, M*D) gradient buffer, so the stacked projection needs no per-layer copies in either direction.
+ * Strides are in elements, >= M*D, multiples of 16 bytes; 0 means dense.  Pointers address element [0, 0, 0, 0] of
+ * the view.  Vector kernels only (head dim 16/32/64/128, not float64), 16-bit values in the default accumulation
+ * mode; otherwise MSDA_ERR_BAD_STRIDE.  `msda_forward` / `msda_backward` are these with both strides 0.
+ */
+int msda_forward_strided(const void* value, long long value_pixel_stride,
+                         const int64_t* spatial_shapes, const int64_t* level_start_index,
+                         const void* sampling_loc, const void* attn_weight, void* output,
+                         int N, int S, int M, int D, int Lq, int L, int P,
+                         int value_dtype, int im2col_step, void* stream);
+
+int msda_backward_strided(const void* value, long long value_pixel_stride,
+                          const int64_t* spatial_shapes, const int64_t* level_start_index,
+                          const void* sampling_loc, const void* attn_weight, const void* grad_output,
+                          void* grad_value, long long grad_value_pixel_stride,
+                          void* grad_sampling_loc, void* grad_attn_weight,
+                          void* scratch, size_t scratch_bytes,
+                          int N, int S, int M, int D, int Lq, int L, int P,
+                          int value_dtype, int im2col_step, int flags, void* stream);
 
 /* Number of kernel launches (not memsets) the last forward/backward call on this thread enqueued;
  * used by bench.py to report `gpu_launches`. */

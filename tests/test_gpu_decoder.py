@@ -1,0 +1,232 @@
+"""GPU tests of the decoder-side work (BASELINE configs[3]):
+* sparse levels of the default 16-bit backward add straight into grad_value (include/msda_b200.h,
+  MSDA_BWD_NO_SPARSE_DIRECT switches it off);
+* the strided entry points read / write a layer's view of a stacked (N, S, K, M, D) projection in place;
+* ``share_value_proj`` (one stacked value_proj GEMM for K cross-attention modules) reproduces K independent modules.
+Tolerances as in test_gpu_parity.py (fp32 1e-5, bf16 2e-2, fp16 5e-3, relative to the oracle tensor's max)."""
+import pytest
+import torch
+
+from tests.helpers import lsi_of, random_problem, rel_to_max
+from tests.test_gpu_parity import TOL, _with_flags, check, ops, oracle_on_rounded_inputs, run_cuda  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+NO_SPARSE = 4        # MSDA_BWD_NO_SPARSE_DIRECT
+
+
+# ---------------------------------------------------------------------------------------------------
+# sparse levels: direct accumulation
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shapes,Lq", [
+    ([(32, 32), (16, 16), (8, 8), (4, 4)], 40),      # levels 0, 1 sparse (2*40*4 <= 1024, 256), levels 2, 3 bucketed
+    ([(32, 32), (16, 16)], 30),                      # every level sparse: the rounding pass has nothing to do
+    ([(6, 4), (3, 2)], 3),                           # tiny, non-square, boundary of the criterion (2*3*4 == 24)
+    ([(20, 12), (5, 3), (40, 24)], 25),              # sparse levels not in order of size
+])
+def test_sparse_levels_add_directly_into_grad_value(ops, dtype, shapes, Lq):
+    problem = random_problem(3, 8, 32, Lq, shapes, 4, seed=5)
+    check(ops, problem, dtype)
+    value, ss, lsi, loc, attn, go = problem
+    fast = run_cuda(ops, value, ss, lsi, loc, attn, go, dtype)
+    bucketed = _with_flags(NO_SPARSE, lambda: run_cuda(ops, value, ss, lsi, loc, attn, go, dtype))
+    # nothing but grad_value depends on the accumulation mode
+    assert torch.equal(fast[0], bucketed[0]) and torch.equal(fast[2], bucketed[2]) and torch.equal(fast[3], bucketed[3])
+    want = oracle_on_rounded_inputs(value, ss, loc, attn, go, dtype)[1]
+    e_fast, e_bucketed = rel_to_max(fast[1], want), rel_to_max(bucketed[1], want)
+    assert e_fast < TOL[dtype] and e_bucketed < TOL[dtype]
+    assert e_fast < 2.5 * max(e_bucketed, 2e-3), (e_fast, e_bucketed)
+
+
+@pytest.mark.parametrize("D", [16, 64, 128])
+def test_sparse_levels_all_vector_head_dims(ops, D):
+    check(ops, random_problem(2, 4, D, 20, [(24, 24), (12, 12), (3, 3)], 3, seed=6), torch.bfloat16)
+
+
+def test_sparse_levels_untouched_rows_are_exact_zeros(ops):
+    """Rows no sampling point touches must come back as exact zeros (the zero pass covers the direct rows, the
+    rounding pass the bucketed ones), with grad_value initialised to garbage by the allocator."""
+    from vision_instance_seg_b200 import MultiScaleDeformableAttention as MSDA
+    dev = "cuda:0"
+    ss = torch.tensor([(16, 16), (4, 4)], dtype=torch.long)
+    N, M, D, Lq, L, P = 2, 8, 32, 8, 2, 4
+    value = torch.randn(N, 272, M, D, device=dev).to(torch.bfloat16)
+    loc = torch.full((N, Lq, M, L, P, 2), 0.5 + 1.0 / 32, device=dev)       # centre of pixel (8, 8) of level 0
+    attn = torch.full((N, Lq, M, L, P), 1.0 / 8, device=dev)
+    go = torch.ones(N, Lq, M * D, dtype=torch.bfloat16, device=dev)
+    torch.empty(N * 272 * M * D, dtype=torch.bfloat16, device=dev).fill_(float("nan"))   # poison the allocator's cache
+    gv, _, _ = MSDA.ms_deform_attn_backward(value, ss.to(dev), lsi_of(ss).to(dev), loc, attn, go, 64)
+    gv = gv.float().view(N, 272, M * D)
+    assert torch.isfinite(gv).all()
+    hit0 = 8 * 16 + 8
+    touched = torch.zeros(272, dtype=torch.bool)
+    touched[hit0] = True
+    touched[256:] = True            # level 1: location (0.53, 0.53) * 4 - 0.5 = 1.625 -> pixels (1..2, 1..2), checked loosely
+    assert float(gv[:, ~touched.to(dev)].abs().max()) == 0.0
+    assert torch.allclose(gv[:, hit0], torch.full_like(gv[:, hit0], Lq * P / 8.0), rtol=1e-2)
+
+
+def test_config4_decoder_shape_uses_direct_levels_and_matches_bucketed(ops):
+    """cfg4 geometry (300 queries against 128^2 .. 16^2): levels 0 and 1 are sparse.  Both accumulation modes must
+    agree with the oracle; 2 images keep the oracle quick."""
+    from vision_instance_seg_b200 import workloads as W
+    cfg = W.CONFIGS["cfg4_decoder_300q_bf16"]
+    v, ss, lsi, loc, attn = W.make_decoder_inputs(cfg["shapes"], 2, torch.bfloat16, queries=300, device="cpu", seed=11)
+    go = torch.randn(2, 300, 256, generator=torch.Generator().manual_seed(8))
+    want = oracle_on_rounded_inputs(v.float(), ss, loc, attn, go, torch.bfloat16)[1]
+    fast = run_cuda(ops, v.float(), ss, lsi, loc, attn, go, torch.bfloat16)[1]
+    bucketed = _with_flags(NO_SPARSE, lambda: run_cuda(ops, v.float(), ss, lsi, loc, attn, go, torch.bfloat16))[1]
+    e_fast, e_bucketed = rel_to_max(fast, want), rel_to_max(bucketed, want)
+    assert e_fast < 2e-2 and e_bucketed < 2e-2
+    assert e_fast < 2.5 * max(e_bucketed, 2e-3), (e_fast, e_bucketed)
+
+
+# ---------------------------------------------------------------------------------------------------
+# strided entry points
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("Lq", [12, 700])          # sparse / bucketed levels for the 16-bit types
+def test_stacked_views_match_dense_copies(ops, dtype, Lq):
+    from vision_instance_seg_b200 import MultiScaleDeformableAttention as MSDA
+    dev = "cuda:0"
+    K, N, M, D, P = 3, 2, 8, 32, 4
+    shapes = [(16, 16), (8, 8), (4, 4)]
+    g = torch.Generator().manual_seed(4)
+    ss = torch.as_tensor(shapes, dtype=torch.long)
+    S = int(ss.prod(1).sum())
+    value_all = torch.randn(N, S, K, M, D, generator=g).to(dev, dtype)
+    _, _, lsi, loc, attn, go = random_problem(N, M, D, Lq, shapes, P, seed=9, dtype=torch.float32)
+    ssd, lsid, loc, attn, go = ss.to(dev), lsi.to(dev), loc.to(dev), attn.to(dev), go.to(dev, dtype)
+    grad_all = torch.full_like(value_all, float("nan"))
+    for layer in range(K):
+        dense = value_all[:, :, layer].contiguous()
+        out_d = MSDA.ms_deform_attn_forward(dense, ssd, lsid, loc, attn, 64)
+        out_s = MSDA.ms_deform_attn_forward_stacked(value_all, layer, ssd, lsid, loc, attn, 64)
+        assert torch.equal(out_d, out_s)
+        gv_d, gl_d, ga_d = MSDA.ms_deform_attn_backward(dense, ssd, lsid, loc, attn, go, 64)
+        gl_s, ga_s = MSDA.ms_deform_attn_backward_stacked(value_all, layer, ssd, lsid, loc, attn, go, grad_all, 64)
+        assert torch.equal(gl_d, gl_s) and torch.equal(ga_d, ga_s)
+        gv_s = grad_all[:, :, layer]
+        if dtype == torch.float32 or Lq == 12:
+            # fp32: order of the reductions differs from run to run; sparse 16-bit: packed adds in value dtype
+            assert rel_to_max(gv_s, gv_d) < (1e-5 if dtype == torch.float32 else TOL[dtype])
+        else:
+            assert rel_to_max(gv_s, gv_d) < TOL[dtype]
+        # the other layers' slices were not touched
+        for other in range(layer + 1, K):
+            assert torch.isnan(grad_all[:, :, other]).all()
+    assert torch.isfinite(grad_all).all()
+
+
+def test_strided_entry_points_validate_strides(ops):
+    import ctypes
+    from vision_instance_seg_b200 import _lib
+    lib = _lib.load_library()
+    dev = "cuda:0"
+    ss = torch.tensor([(4, 4)], dtype=torch.long, device=dev)
+    lsi = torch.zeros(1, dtype=torch.long, device=dev)
+    v = torch.zeros(1, 16, 2, 8, 32, device=dev)
+    loc = torch.zeros(1, 2, 8, 1, 4, 2, device=dev)
+    attn = torch.zeros(1, 2, 8, 1, 4, device=dev)
+    out = torch.zeros(1, 2, 256, device=dev)
+
+    def fwd(stride, D=32, dtype=_lib.MSDA_F32):
+        return lib.msda_forward_strided(v.data_ptr(), stride, ss.data_ptr(), lsi.data_ptr(), loc.data_ptr(), attn.data_ptr(),
+                                        out.data_ptr(), 1, 16, 8, D, 2, 1, 4, dtype, 64, None)
+    assert fwd(512) == 0 and fwd(0) == 0
+    assert fwd(255) == -8 and fwd(258) == -8            # < M*D; not a multiple of 16 bytes
+    assert fwd(2 * 8 * 30, D=30) == -8                   # compatibility kernels are dense only
+    assert fwd(512, dtype=_lib.MSDA_F64) == -8
+    assert b"stride" in lib.msda_error_string(-8)
+    torch.cuda.synchronize()
+
+
+# ---------------------------------------------------------------------------------------------------
+# share_value_proj: K cross-attention modules on one stacked GEMM
+# ---------------------------------------------------------------------------------------------------
+def _decoder_like_inputs(N, Lq, shapes, dev, seed):
+    g = torch.Generator().manual_seed(seed)
+    ss = torch.as_tensor(shapes, dtype=torch.long)
+    S = int(ss.prod(1).sum())
+    src = torch.randn(N, S, 256, generator=g).to(dev)
+    mask = (torch.rand(N, S, generator=g) < 0.1).to(dev)
+    queries = [torch.randn(N, Lq, 256, generator=g).to(dev) for _ in range(3)]
+    ref = torch.cat([torch.rand(N, Lq, 1, 2, generator=g).expand(-1, -1, len(shapes), -1),
+                     torch.rand(N, Lq, 1, 2, generator=g).expand(-1, -1, len(shapes), -1) * 0.4 + 0.05], -1).contiguous().to(dev)
+    return ss.to(dev), lsi_of(ss).to(dev), src, mask, queries, ref
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+def test_shared_value_proj_matches_independent_modules(ops, autocast):
+    import copy
+    from vision_instance_seg_b200.modules import MSDeformAttn, share_value_proj
+    dev = "cuda:0"
+    torch.manual_seed(0)
+    K, N, Lq = 3, 2, 50
+    shapes = [(16, 16), (8, 8), (4, 4), (2, 2)]
+    ss, lsi, src, mask, queries, ref = _decoder_like_inputs(N, Lq, shapes, dev, 1)
+    mods = [MSDeformAttn(256, 4, 8, 4).to(dev) for _ in range(K)]
+    for m in mods:                       # non-trivial offsets / attention so that the layers differ
+        torch.nn.init.normal_(m.sampling_offsets.weight, std=0.02)
+        torch.nn.init.normal_(m.attention_weights.weight, std=0.05)
+    shared_mods = copy.deepcopy(mods)
+    share_value_proj(shared_mods)
+
+    def run(modules):
+        s = src.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            x = 0
+            for m, q in zip(modules, queries):
+                x = x + m(q + x, ref, s, ss, lsi, mask)     # layer i's query depends on layer i-1's output
+            loss = (x.float() ** 2).mean()
+        loss.backward()
+        return x.detach().float(), s.grad, [p.grad for m in modules for p in m.parameters()]
+
+    out_a, gs_a, gp_a = run(mods)
+    out_b, gs_b, gp_b = run(shared_mods)
+    tol = 2e-2 if autocast else 1e-4
+    assert rel_to_max(out_b, out_a) < tol
+    assert rel_to_max(gs_b, gs_a) < tol
+    for a, b in zip(gp_a, gp_b):
+        assert b is not None and rel_to_max(b, a) < (5e-2 if autocast else 1e-4)
+    # parameter names / state_dict are untouched
+    assert list(shared_mods[0].state_dict().keys()) == list(mods[0].state_dict().keys())
+    # a second pass (fresh gradient buffer) and inference mode work as well
+    out_c, _, _ = run(shared_mods)
+    assert torch.equal(out_b, out_c)
+    with torch.no_grad():
+        y = shared_mods[0](queries[0], ref, src, ss, lsi, mask)
+        z = mods[0](queries[0], ref, src, ss, lsi, mask)
+    assert rel_to_max(y, z) < 1e-4
+
+
+def test_shared_value_proj_partial_use_and_double_use(ops):
+    """Only some of the K layers contribute to the loss / one layer is used twice: the gradient is still exact."""
+    import copy
+    from vision_instance_seg_b200.modules import MSDeformAttn, share_value_proj
+    dev = "cuda:0"
+    torch.manual_seed(1)
+    ss, lsi, src, mask, queries, ref = _decoder_like_inputs(1, 20, [(8, 8), (4, 4), (2, 2), (1, 1)], dev, 2)
+    mods = [MSDeformAttn(256, 4, 8, 4).to(dev) for _ in range(3)]
+    shared_mods = copy.deepcopy(mods)
+    share_value_proj(shared_mods)
+
+    def run(modules, pattern):
+        s = src.clone().requires_grad_(True)
+        outs = [modules[i](queries[i], ref, s, ss, lsi, None) for i in range(3)]
+        loss = sum((outs[i] ** 2).mean() * w for i, w in pattern)
+        loss.backward()
+        return s.grad, [m.value_proj.weight.grad for m in modules]
+
+    for pattern in ([(0, 1.0), (2, 0.5)], [(1, 1.0), (1, 2.0)], [(0, 1.0), (1, 1.0), (2, 1.0)]):
+        for m in mods + shared_mods:
+            m.zero_grad(set_to_none=True)
+        gs_a, gw_a = run(mods, pattern)
+        gs_b, gw_b = run(shared_mods, pattern)
+        assert rel_to_max(gs_b, gs_a) < 1e-4
+        for a, b in zip(gw_a, gw_b):
+            if a is None:
+                assert b is None or float(b.abs().max()) == 0.0
+            else:
+                assert rel_to_max(b, a) < 1e-4

@@ -26,7 +26,8 @@ _DTYPES = {torch.float32: _lib.MSDA_F32, torch.float64: _lib.MSDA_F64,
 #: backward flags (see include/msda_b200.h); MSDA_B200_FP32_ACCUM=1 forces fp32 accumulation of grad_value for
 #: 16-bit values, MSDA_B200_ACCUM_DEPTH=<n> overrides the fp16 bucket depth
 backward_flags = (_lib.MSDA_BWD_GRAD_VALUE_FP32_ACCUM if os.environ.get("MSDA_B200_FP32_ACCUM") == "1"
-                  else _lib.MSDA_BWD_DEFAULT) | _lib.accum_depth_flag(int(os.environ.get("MSDA_B200_ACCUM_DEPTH", "0")))
+                  else _lib.MSDA_BWD_DEFAULT) | _lib.accum_depth_flag(int(os.environ.get("MSDA_B200_ACCUM_DEPTH", "0"))) \
+    | (_lib.MSDA_BWD_NO_SPARSE_DIRECT if os.environ.get("MSDA_B200_NO_SPARSE_DIRECT") == "1" else 0)
 
 
 def _require(t: torch.Tensor, name: str) -> None:
@@ -115,6 +116,97 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     if grad_attn.dtype != attn_weight.dtype:
         grad_attn = grad_attn.to(attn_weight.dtype)
     return [grad_value, grad_loc, grad_attn]
+
+
+# ---------------------------------------------------------------------------------------------------
+# Strided value views (opt-in; SURVEY.md §8f rank 2: one stacked ``value_proj`` GEMM for all decoder layers).
+# ``value_all`` is a contiguous (N, S, K, M, D) tensor -- the output of a Linear whose weight stacks the K layers'
+# ``value_proj`` weights -- and ``layer`` picks the view [:, :, layer] that the kernels read in place; the backward
+# writes grad_value into the same view of ``grad_value_all``.  Not part of the upstream extension.
+# ---------------------------------------------------------------------------------------------------
+def _stacked_dims(value_all, layer, spatial_shapes, sampling_loc):
+    if value_all.dim() != 5 or sampling_loc.dim() != 6:
+        raise RuntimeError("value_all must be (N, S, K, M, D) and sampling_loc (N, Lq, M, L, P, 2)")
+    N, S, K, M, D = value_all.shape
+    if not 0 <= int(layer) < K:
+        raise RuntimeError(f"layer {layer} out of range for {K} stacked projections")
+    _, Lq, M2, L, P, two = sampling_loc.shape
+    if M2 != M or two != 2 or spatial_shapes.shape[0] != L or sampling_loc.shape[0] != N:
+        raise RuntimeError("inconsistent shapes between value_all, spatial_shapes and sampling_loc")
+    return N, S, K, M, D, Lq, L, P
+
+
+def ms_deform_attn_forward_stacked(value_all, layer, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                   im2col_step):
+    """``ms_deform_attn_forward`` on ``value_all[:, :, layer]`` without materialising the view."""
+    for t, n in ((value_all, "value_all"), (spatial_shapes, "spatial_shapes"), (level_start_index, "level_start_index"),
+                 (sampling_loc, "sampling_loc"), (attn_weight, "attn_weight")):
+        _require(t, n)
+    if value_all.dtype not in _DTYPES:
+        raise RuntimeError(f"ms_deform_attn_forward_stacked not implemented for '{value_all.dtype}'")
+    N, S, K, M, D, Lq, L, P = _stacked_dims(value_all, layer, spatial_shapes, sampling_loc)
+    aux = _aux_dtype(value_all)
+    loc = sampling_loc if sampling_loc.dtype == aux else sampling_loc.to(aux)
+    attn = attn_weight if attn_weight.dtype == aux else attn_weight.to(aux)
+    shapes = _meta(spatial_shapes, value_all.device)
+    lsi = _meta(level_start_index, value_all.device)
+    lib = _lib.load_library()
+    with torch.cuda.device(value_all.device):
+        out = torch.empty((N, Lq, M * D), dtype=value_all.dtype, device=value_all.device)
+        if out.numel() == 0:
+            return out
+        stream = torch.cuda.current_stream().cuda_stream
+        base = value_all.data_ptr() + int(layer) * M * D * value_all.element_size()
+        rc = lib.msda_forward_strided(base, K * M * D, shapes.data_ptr(), lsi.data_ptr(), loc.data_ptr(), attn.data_ptr(),
+                                      out.data_ptr(), N, S, M, D, Lq, L, P, _DTYPES[value_all.dtype], int(im2col_step),
+                                      stream)
+    _lib.check(rc, "ms_deform_attn_forward_stacked")
+    return out
+
+
+def ms_deform_attn_backward_stacked(value_all, layer, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                    grad_output, grad_value_all, im2col_step):
+    """``ms_deform_attn_backward`` on ``value_all[:, :, layer]``; ``grad_value_all[:, :, layer]`` is fully overwritten in
+    place (every other layer's slice is left untouched).  -> [grad_sampling_loc, grad_attn_weight]"""
+    for t, n in ((value_all, "value_all"), (spatial_shapes, "spatial_shapes"), (level_start_index, "level_start_index"),
+                 (sampling_loc, "sampling_loc"), (attn_weight, "attn_weight"), (grad_output, "grad_output"),
+                 (grad_value_all, "grad_value_all")):
+        _require(t, n)
+    if value_all.dtype not in _DTYPES:
+        raise RuntimeError(f"ms_deform_attn_backward_stacked not implemented for '{value_all.dtype}'")
+    if grad_value_all.shape != value_all.shape or grad_value_all.dtype != value_all.dtype:
+        raise RuntimeError("grad_value_all must match value_all in shape and dtype")
+    N, S, K, M, D, Lq, L, P = _stacked_dims(value_all, layer, spatial_shapes, sampling_loc)
+    aux = _aux_dtype(value_all)
+    loc = sampling_loc if sampling_loc.dtype == aux else sampling_loc.to(aux)
+    attn = attn_weight if attn_weight.dtype == aux else attn_weight.to(aux)
+    go = grad_output if grad_output.dtype == value_all.dtype else grad_output.to(value_all.dtype)
+    shapes = _meta(spatial_shapes, value_all.device)
+    lsi = _meta(level_start_index, value_all.device)
+    lib = _lib.load_library()
+    code = _DTYPES[value_all.dtype]
+    flags = backward_flags & ~_lib.MSDA_BWD_GRAD_VALUE_FP32_ACCUM      # strided grad_value: default accumulation only
+    with torch.cuda.device(value_all.device):
+        grad_loc = torch.empty(sampling_loc.shape, dtype=aux, device=value_all.device)
+        grad_attn = torch.empty(attn_weight.shape, dtype=aux, device=value_all.device)
+        if grad_loc.numel() == 0 or value_all.numel() == 0:
+            grad_value_all[:, :, int(layer)].zero_()
+            return [grad_loc.zero_(), grad_attn.zero_()]
+        nbytes = lib.msda_backward_scratch_bytes(N, S, M, D, Lq, L, P, code, flags)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=value_all.device) if nbytes else None
+        stream = torch.cuda.current_stream().cuda_stream
+        off = int(layer) * M * D * value_all.element_size()
+        rc = lib.msda_backward_strided(value_all.data_ptr() + off, K * M * D, shapes.data_ptr(), lsi.data_ptr(),
+                                       loc.data_ptr(), attn.data_ptr(), go.data_ptr(),
+                                       grad_value_all.data_ptr() + off, K * M * D, grad_loc.data_ptr(), grad_attn.data_ptr(),
+                                       scratch.data_ptr() if scratch is not None else None, nbytes,
+                                       N, S, M, D, Lq, L, P, code, int(im2col_step), flags, stream)
+    _lib.check(rc, "ms_deform_attn_backward_stacked")
+    if grad_loc.dtype != sampling_loc.dtype:
+        grad_loc = grad_loc.to(sampling_loc.dtype)
+    if grad_attn.dtype != attn_weight.dtype:
+        grad_attn = grad_attn.to(attn_weight.dtype)
+    return [grad_loc, grad_attn]
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -19,7 +19,8 @@ the built library or without a CUDA device raises.
 from . import MultiScaleDeformableAttention  # noqa: F401
 from ._lib import library_path, load_library  # noqa: F401
 from .functions import MSDeformAttnFunction, MSDeformAttnFusedFunction  # noqa: F401
-from .modules import MSDeformAttn, set_fused_encoder_layers, set_fused_preop  # noqa: F401
+from .modules import (MSDeformAttn, set_fused_encoder_layers, set_fused_preop, share_value_proj,  # noqa: F401
+                      unshare_value_proj)
 
 
 
@@ -41,4 +42,4 @@ def install_as_upstream_extension(name: str = "MultiScaleDeformableAttention"):
 
 
 __all__ = ["MSDeformAttn", "MSDeformAttnFunction", "MSDeformAttnFusedFunction", "MultiScaleDeformableAttention",
-           "set_fused_preop", "set_fused_encoder_layers", "install_as_upstream_extension", "load_library", "library_path"]
+           "set_fused_preop", "set_fused_encoder_layers", "share_value_proj", "unshare_value_proj", "install_as_upstream_extension", "load_library", "library_path"]

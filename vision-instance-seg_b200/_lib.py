@@ -18,6 +18,7 @@ _lib = None
 MSDA_F32, MSDA_F64, MSDA_BF16, MSDA_F16 = 0, 1, 2, 3
 MSDA_BWD_DEFAULT = 0
 MSDA_BWD_GRAD_VALUE_FP32_ACCUM = 2
+MSDA_BWD_NO_SPARSE_DIRECT = 4
 
 
 def accum_depth_flag(depth: int) -> int:
@@ -31,6 +32,8 @@ EXPORTED_SYMBOLS = (
     "msda_forward",
     "msda_backward_scratch_bytes",
     "msda_backward",
+    "msda_forward_strided",
+    "msda_backward_strided",
     "msda_last_launch_count",
     "msda_total_launch_count",
     "msda_profile_enable",
@@ -68,6 +71,11 @@ def _declare(lib):
     lib.msda_backward.restype = i
     lib.msda_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, vp, vp, vp, vp, sz,
                                   i, i, i, i, i, i, i, i, i, i, vp]
+    lib.msda_forward_strided.restype = i
+    lib.msda_forward_strided.argtypes = [vp, ctypes.c_longlong, i64p, i64p, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]
+    lib.msda_backward_strided.restype = i
+    lib.msda_backward_strided.argtypes = [vp, ctypes.c_longlong, i64p, i64p, vp, vp, vp, vp, ctypes.c_longlong, vp, vp, vp, sz,
+                                          i, i, i, i, i, i, i, i, i, i, vp]
     lib.msda_fused_supported.restype = i
     lib.msda_fused_supported.argtypes = [i, i]
     lib.msda_fused_forward.restype = i

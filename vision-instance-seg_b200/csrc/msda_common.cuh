@@ -93,9 +93,11 @@ struct LevelMeta {
   int W[kMaxLevels];
   int start[kMaxLevels];
   // bucketed fp16 accumulation of grad_value (see AccumLayout below)
-  int accK[kMaxLevels];      // number of private copies ("buckets") of the level
+  int accK[kMaxLevels];      // number of private copies ("buckets") of the level; 0 = sparse level, added directly
   int accBase[kMaxLevels];   // first pixel row of the level's bucket 0 inside one image of the accumulator
   int accStride;             // pixel rows per image of the accumulator
+  int dirOff[kMaxLevels];    // sparse levels: first row of the level among one image's directly accumulated rows
+  int dirRows;               // directly accumulated pixel rows per image
 };
 
 __device__ __forceinline__ void load_level_meta(LevelMeta& meta, const int64_t* __restrict__ shapes,
@@ -116,6 +118,14 @@ __device__ __forceinline__ void load_level_meta(LevelMeta& meta, const int64_t* 
 // (q mod K_l), and the rounding pass sums the copies in fp32.  expected adds = ceil(Lq*P / (H_l*W_l)).
 // Everything is derived on the device from the int64 shape tensor; the host only needs the upper bound
 // accum_rows_bound() to size the buffer.
+//
+// Sparse levels (decoder cross-attention: a few hundred queries against 10^4 pixels).  When a level expects at most
+// one corner row per two pixel rows (four corner rows per point: 4*Lq*P <= 2*H_l*W_l) almost every element receives
+// zero or one add, and a packed 16-bit add straight into grad_value is then as accurate as accumulating anywhere
+// else and rounding once.  Such a level gets K_l = 0: its contributions are added, unscaled, into the (zeroed)
+// grad_value rows in the value dtype, it owns no accumulator rows, and the rounding pass skips it -- the dense zero /
+// sum / round traffic of the fp16 accumulator (which dominates a decoder layer's backward) is paid only for the
+// coarse levels.
 // ---------------------------------------------------------------------------------------------------
 __host__ __device__ inline long long accum_rows_bound(int S, int L, int Lq, int P, int depth) {
   const long long per_level = (static_cast<long long>(Lq) * P + depth - 1) / depth;
@@ -123,18 +133,22 @@ __host__ __device__ inline long long accum_rows_bound(int S, int L, int Lq, int 
 }
 
 // call after load_level_meta (thread 0 fills, then a barrier)
-__device__ __forceinline__ void build_accum_layout(LevelMeta& meta, int L, int Lq, int P, int depth) {
+__device__ __forceinline__ void build_accum_layout(LevelMeta& meta, int L, int Lq, int P, int depth, bool sparse_direct) {
   if (threadIdx.x == 0) {
-    int base = 0;
+    int base = 0, dir = 0;
     for (int l = 0; l < L; ++l) {
       const long long hw = static_cast<long long>(meta.H[l]) * meta.W[l];
       const long long adds = hw > 0 ? (static_cast<long long>(Lq) * P + hw - 1) / hw : 1;
       const int K = static_cast<int>((adds + depth - 1) / depth);
-      meta.accK[l] = K < 1 ? 1 : K;
+      const bool direct = sparse_direct && hw > 0 && 2ll * Lq * P <= hw;
+      meta.accK[l] = direct ? 0 : (K < 1 ? 1 : K);
       meta.accBase[l] = base;
+      meta.dirOff[l] = dir;
       base += meta.accK[l] * static_cast<int>(hw);
+      if (direct) dir += static_cast<int>(hw);
     }
     meta.accStride = base;
+    meta.dirRows = dir;
   }
   __syncthreads();
 }

@@ -232,7 +232,9 @@ __global__ void __launch_bounds__(kThreads)
 msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const AT* __restrict__ loc,
                     const AT* __restrict__ attn, const float* __restrict__ ref, int R, T* __restrict__ out,
-                    int S, int M, int Lq, int L, int P, int total_pairs) {
+                    int S, int M, int Lq, int L, int P, int total_pairs, int vps) {
+  // vps: elements between neighbouring pixels of `value` (M*D when dense; larger when the projections of several
+  // layers are interleaved per pixel, see msda_forward_strided)
   constexpr int VEC = 16 / sizeof(T);
   constexpr int G = D / VEC;        // lanes per (b, q, m) pair
   constexpr int GPW = 32 / G;       // pairs per warp
@@ -273,8 +275,8 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   const int pair = pair0 + g;
   const int m = pair % M;
   const int b = (pair / M) / Lq;
-  const uint32_t pix_bytes = static_cast<uint32_t>(M) * D * sizeof(T);        // bytes between neighbouring pixels
-  const char* vb = reinterpret_cast<const char*>(value) + (static_cast<size_t>(b) * S * M + m) * (D * sizeof(T)) + c * 16;
+  const uint32_t pix_bytes = static_cast<uint32_t>(vps) * sizeof(T);          // bytes between neighbouring pixels
+  const char* vb = reinterpret_cast<const char*>(value) + (static_cast<size_t>(b) * S * vps + m * D) * sizeof(T) + c * 16;
   const float* myloc = ws.loc + g * ws.loc_stride;
   const float* myattn = ws.attn + g * ws.attn_stride;
 
@@ -380,9 +382,12 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
                     const int64_t* __restrict__ lsi, const AT* __restrict__ loc,
                     const AT* __restrict__ attn, const float* __restrict__ ref, int R,
                     const T* __restrict__ grad_out,
-                    float* __restrict__ gv32, __half* __restrict__ gv16, const uint32_t* __restrict__ ctrl,
+                    float* __restrict__ gv32, __half* __restrict__ gv16, T* __restrict__ gv_direct,
+                    const uint32_t* __restrict__ ctrl,
                     AT* __restrict__ grad_loc, AT* __restrict__ grad_attn,
-                    int S, int M, int Lq, int L, int P, int total_pairs, int depth) {
+                    int S, int M, int Lq, int L, int P, int total_pairs, int depth, int vps, int gps) {
+  // vps: elements between neighbouring pixels of `value`; gps: the same for the buffer laid out like value that receives
+  // reductions directly (gv32, or gv_direct for the sparse levels of GV16 mode: see build_accum_layout)
   constexpr int VEC = 16 / sizeof(T);
   constexpr int G = D / VEC;
   constexpr int GPW = 32 / G;
@@ -393,7 +398,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   extern __shared__ __align__(16) float smem[];
   __shared__ LevelMeta meta;
   load_level_meta(meta, shapes, lsi, L);
-  if constexpr (GV16) build_accum_layout(meta, L, Lq, P, depth);
+  if constexpr (GV16) build_accum_layout(meta, L, Lq, P, depth, gv_direct != nullptr);
 
   const int LP = L * P;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -422,9 +427,9 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   const int pair = pair0 + (active ? g : 0);
   const int m = pair % M;
   const int b = (pair / M) / Lq;
-  const uint32_t pix_bytes = static_cast<uint32_t>(M) * D * sizeof(T);
-  const size_t img_pix = static_cast<size_t>(b) * S * M + m;                     // in units of head slices
-  const char* vb = reinterpret_cast<const char*>(value) + img_pix * (D * sizeof(T)) + c * 16;
+  const uint32_t pix_bytes = static_cast<uint32_t>(vps) * sizeof(T);
+  const size_t img_pix = static_cast<size_t>(b) * S * M + m;                     // in units of head slices (dense layout)
+  const char* vb = reinterpret_cast<const char*>(value) + (static_cast<size_t>(b) * S * vps + m * D) * sizeof(T) + c * 16;
   float* myloc = ws.loc + (active ? g : 0) * ws.loc_stride;
   float* myattn = ws.attn + (active ? g : 0) * ws.attn_stride;
   float* mygattn = nullptr;
@@ -453,14 +458,20 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   }
   // element offset of this lane's first scatter channel inside a head slice
   const int sc0 = (k16 && !GV16) ? 4 * c : c * VEC;
-  float* gv32_base = gv32 + img_pix * D + sc0;
+  float* gv32_base = gv32 + (static_cast<size_t>(b) * S * gps + m * D) + sc0;
   const int q = (pair / M) % Lq;
   // bucketed fp16 accumulator: image b starts at row b*accStride; the head / channel offset is the same
   __half* gv16_base = nullptr;
+  T* gvd_base = nullptr;                  // sparse levels: this lane's channels of image b in grad_value itself
   size_t acc_row = 0;                     // first accumulator row of (this query's bucket of) the current level
+  bool direct = false;                    // current level is sparse: add straight into grad_value (warp-uniform)
+  float gv_unscale = 1.f;
   if constexpr (GV16) {
     gv16_base = gv16 + (static_cast<size_t>(b) * meta.accStride * M + m) * D + c * VEC;
-    acc_row = static_cast<size_t>(meta.accBase[0]) + static_cast<size_t>(q % meta.accK[0]) * (meta.H[0] * meta.W[0]);
+    gvd_base = gv_direct + (static_cast<size_t>(b) * S * gps + m * D) + c * VEC;
+    direct = meta.accK[0] == 0;
+    acc_row = static_cast<size_t>(meta.accBase[0]) + static_cast<size_t>(direct ? 0 : q % meta.accK[0]) * (meta.H[0] * meta.W[0]);
+    gv_unscale = 1.f / gv_scale;          // exact: power of two
 #pragma unroll
     for (int i = 0; i < VEC; ++i) go_s[i] *= gv_scale;      // exact: power-of-two scale
   }
@@ -497,12 +508,18 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (w[k] != 0.f) {            // invalid corners (and exact-zero weights) add nothing
-              const size_t e = (lvl_pix + idx[k]) * pix_elems;
+              const size_t e = (lvl_pix + idx[k]) * static_cast<size_t>(gps);
               float r[VEC];
 #pragma unroll
               for (int i = 0; i < VEC; ++i) r[i] = w[k] * go_s[i];
               if constexpr (GV16) {
-                red_add_16bit_x8<__half>(gv16_base + (acc_row + idx[k]) * pix_elems, pack16<__half>(r));
+                if (direct) {             // sparse level: unscaled, in the value dtype, into grad_value
+#pragma unroll
+                  for (int i = 0; i < VEC; ++i) r[i] *= gv_unscale;
+                  red_add_16bit_x8<T>(gvd_base + e, pack16<T>(r));
+                } else {
+                  red_add_16bit_x8<__half>(gv16_base + (acc_row + idx[k]) * pix_elems, pack16<__half>(r));
+                }
               } else if constexpr (k16) {
                 red_add_f32x4(gv32_base + e, r[0], r[1], r[2], r[3]);
                 red_add_f32x4(gv32_base + e + D / 2, r[4], r[5], r[6], r[7]);
@@ -524,8 +541,10 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
           if (l < L) {
             H = meta.H[l]; W = meta.W[l]; Hf = static_cast<float>(H); Wf = static_cast<float>(W);
             lvl_pix = static_cast<size_t>(meta.start[l]);
-            if constexpr (GV16)
-              acc_row = static_cast<size_t>(meta.accBase[l]) + static_cast<size_t>(q % meta.accK[l]) * (H * W);
+            if constexpr (GV16) {
+              direct = meta.accK[l] == 0;
+              acc_row = static_cast<size_t>(meta.accBase[l]) + static_cast<size_t>(direct ? 0 : q % meta.accK[l]) * (H * W);
+            }
           }
         }
       } else {
@@ -607,19 +626,36 @@ msda_absmax_kernel(const T* __restrict__ x, size_t n8, uint32_t* __restrict__ ct
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(ctrl, __float_as_uint(m));
 }
 
-// zero the control block and the rows of the bucketed fp16 accumulator that the device-side layout actually uses
-// (the host only knows the upper bound accum_rows_bound(); for few queries the layout is ~half of it)
+// zero the control block, the rows of the bucketed fp16 accumulator that the device-side layout actually uses
+// (the host only knows the upper bound accum_rows_bound(); for few queries the layout is ~half of it) and, when
+// `gv` is given, the grad_value rows of the sparse levels, which receive their reductions directly
+// (16-bit element types only: 8 elements per 16-byte vector; gps = elements between neighbouring pixels of gv)
 static __global__ void __launch_bounds__(256)
 msda_zero_f16_buckets_kernel(uint4* __restrict__ scratch, size_t ctrl_vecs, const int64_t* __restrict__ shapes,
-                             const int64_t* __restrict__ lsi, int N, int M, int D, int Lq, int L, int P, int depth) {
+                             const int64_t* __restrict__ lsi, uint16_t* __restrict__ gv, int N, int S, int M, int D,
+                             int Lq, int L, int P, int depth, int gps) {
   __shared__ LevelMeta meta;
   load_level_meta(meta, shapes, lsi, L);
-  build_accum_layout(meta, L, Lq, P, depth);
-  const size_t total = ctrl_vecs + static_cast<size_t>(N) * meta.accStride * (static_cast<size_t>(M) * D / 8);
+  build_accum_layout(meta, L, Lq, P, depth, gv != nullptr);
+  const size_t vpp = static_cast<size_t>(M) * D / 8;                 // 16-byte vectors per pixel row
+  const size_t total = ctrl_vecs + static_cast<size_t>(N) * meta.accStride * vpp;
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    scratch[i] = z;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthr = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = tid; i < total; i += nthr) scratch[i] = z;
+  if (meta.dirRows > 0) {
+    const size_t per_img = static_cast<size_t>(meta.dirRows) * vpp;
+    const size_t dtotal = static_cast<size_t>(N) * per_img;
+    for (size_t i = tid; i < dtotal; i += nthr) {
+      const size_t b = i / per_img, j = i - b * per_img;
+      const int r = static_cast<int>(j / vpp), v = static_cast<int>(j - static_cast<size_t>(r) * vpp);
+      int l = 0;                                                     // sparse level that owns direct row r
+      for (int k = 0; k < L; ++k)
+        if (meta.accK[k] == 0 && r >= meta.dirOff[k]) l = k;
+      const size_t pix = b * S + meta.start[l] + (r - meta.dirOff[l]);
+      *reinterpret_cast<uint4*>(gv + pix * gps + v * 8) = z;
+    }
+  }
 }
 
 // bucketed, scaled fp16 accumulation buffer -> 16-bit grad_value: sum the K_l copies in fp32, unscale, round once
@@ -627,10 +663,10 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 msda_round_f16_buckets_kernel(const __half* __restrict__ acc, T* __restrict__ dst, const int64_t* __restrict__ shapes,
                               const int64_t* __restrict__ lsi, const uint32_t* __restrict__ ctrl,
-                              int N, int S, int M, int D, int Lq, int L, int P, int depth) {
+                              int N, int S, int M, int D, int Lq, int L, int P, int depth, int sparse_direct, int gps) {
   __shared__ LevelMeta meta;
   load_level_meta(meta, shapes, lsi, L);
-  build_accum_layout(meta, L, Lq, P, depth);
+  build_accum_layout(meta, L, Lq, P, depth, sparse_direct != 0);
   const float inv = 1.f / f16_accum_scale(ctrl, Lq);        // exact: power of two
   const int vec_per_pix = M * D / 8;
   const size_t total = static_cast<size_t>(N) * S * vec_per_pix;
@@ -642,6 +678,7 @@ msda_round_f16_buckets_kernel(const __half* __restrict__ acc, T* __restrict__ ds
     const int s = static_cast<int>(pix - static_cast<size_t>(b) * S);
     int l = 0;
     while (l + 1 < L && s >= meta.start[l + 1]) ++l;
+    if (meta.accK[l] == 0) continue;      // sparse level: grad_value already holds the sums
     const int hw = meta.H[l] * meta.W[l];
     const size_t row0 = static_cast<size_t>(b) * meta.accStride + meta.accBase[l] + (s - meta.start[l]);
     float sum[8];
@@ -655,7 +692,7 @@ msda_round_f16_buckets_kernel(const __half* __restrict__ acc, T* __restrict__ ds
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) sum[j] *= inv;
-    reinterpret_cast<uint4*>(dst)[i] = pack16<T>(sum);
+    *reinterpret_cast<uint4*>(dst + pix * gps + v * 8) = pack16<T>(sum);
   }
 }
 
@@ -848,7 +885,21 @@ struct Problem {
   const float* ref = nullptr;   // fused pre-op: reference points (N, Lq, L, R); nullptr = plain operator
   int R = 0;
   bool aux16 = false;           // fused pre-op only: offsets / logits (and their gradients) are in the 16-bit value type
+  long long vps = 0, gps = 0;   // elements between neighbouring pixels of value / grad_value (0 = dense, M*D)
+  int value_stride() const { return static_cast<int>(vps > 0 ? vps : static_cast<long long>(M) * D); }
+  int grad_stride() const { return static_cast<int>(gps > 0 ? gps : static_cast<long long>(M) * D); }
+  bool strided() const { return value_stride() != M * D || grad_stride() != M * D; }
 };
+
+// pixel strides of the *_strided entry points: at least one dense pixel row, whole 16-byte vectors
+static int validate_strides(const Problem& pr, size_t elem_bytes) {
+  const long long dense = static_cast<long long>(pr.M) * pr.D;
+  for (long long st : {pr.vps, pr.gps}) {
+    if (st == 0) continue;
+    if (st < dense || st >= (1ll << 31) || (st * static_cast<long long>(elem_bytes)) % 16 != 0) return MSDA_ERR_BAD_STRIDE;
+  }
+  return MSDA_OK;
+}
 
 static int validate(const Problem& pr, int dtype, int im2col_step) {
   if (pr.N <= 0 || pr.S <= 0 || pr.M <= 0 || pr.D <= 0 || pr.Lq <= 0 || pr.L <= 0 || pr.P <= 0) return MSDA_ERR_BAD_SHAPE;
@@ -868,7 +919,8 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // vector kernels: head dims with power-of-two lane groups, and per-image byte offsets that fit 32 bits
 template <typename T> static bool vec_supported(const Problem& pr) {
   const bool d_ok = pr.D == 16 || pr.D == 32 || pr.D == 64 || pr.D == 128;
-  return d_ok && static_cast<unsigned long long>(pr.S) * pr.M * pr.D * sizeof(float) < (1ull << 32);
+  const unsigned long long row = static_cast<unsigned long long>(std::max(pr.value_stride(), pr.grad_stride()));
+  return d_ok && static_cast<unsigned long long>(pr.S) * row * sizeof(float) < (1ull << 32);
 }
 
 // per warp: GPW rows of loc (2*LP + 4 floats) and attn (LP + 4); fused backward adds a gattn row per pair; fused kernels
@@ -903,7 +955,7 @@ static int launch_fwd_vec_impl(const Problem& pr, const void* value, const int64
   ScopedKernelTimer timer(MSDA_KERNEL_FORWARD, st);
   msda_fwd_vec_kernel<T, D, FUSED, AT><<<grid, kThreads, smem, st>>>(
       static_cast<const T*>(value), shapes, lsi, static_cast<const AT*>(loc), static_cast<const AT*>(attn),
-      pr.ref, pr.R, static_cast<T*>(out), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs);
+      pr.ref, pr.R, static_cast<T*>(out), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, pr.value_stride());
   ++g_last_launches, ++g_total_launches;
   return static_cast<int>(cudaGetLastError());
 }
@@ -932,6 +984,7 @@ MSDA_LAUNCHER int launch_fwd(const Problem& pr, const void* value, const int64_t
     }
   }
   if (pr.ref) return MSDA_ERR_FUSED_UNSUPPORTED;
+  if (pr.strided()) return MSDA_ERR_BAD_STRIDE;         // the compatibility kernels read dense values only
   using Aux = typename Traits<T>::Aux;
   const int grid = (pr.total_pairs + kWarps - 1) / kWarps;
   msda_fwd_any_kernel<T><<<grid, kThreads, 0, st>>>(
@@ -944,6 +997,7 @@ MSDA_LAUNCHER int launch_fwd(const Problem& pr, const void* value, const int64_t
 template <typename T, int D, bool FUSED, typename AT>
 static int launch_bwd_vec_impl(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
                                const void* loc, const void* attn, const void* go, float* gv32, __half* gv16,
+                               void* gv_direct, int gv_stride,
                                const uint32_t* ctrl, void* gloc, void* gattn, bool use16, int depth, cudaStream_t st) {
   constexpr int GPW = 32 / (D / (16 / static_cast<int>(sizeof(T))));
   const size_t smem = vec_smem_bytes<T, D>(pr.L, pr.P, FUSED, true);
@@ -958,8 +1012,8 @@ static int launch_bwd_vec_impl(const Problem& pr, const void* value, const int64
       ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD, st);
       msda_bwd_vec_kernel<T, D, true, FUSED, AT><<<grid, kThreads, smem, st>>>(
           static_cast<const T*>(value), shapes, lsi, static_cast<const AT*>(loc), static_cast<const AT*>(attn),
-          pr.ref, pr.R, static_cast<const T*>(go), nullptr, gv16, ctrl, static_cast<AT*>(gloc),
-          static_cast<AT*>(gattn), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth);
+          pr.ref, pr.R, static_cast<const T*>(go), nullptr, gv16, static_cast<T*>(gv_direct), ctrl, static_cast<AT*>(gloc),
+          static_cast<AT*>(gattn), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth, pr.value_stride(), gv_stride);
       ++g_last_launches, ++g_total_launches;
       return static_cast<int>(cudaGetLastError());
     }
@@ -969,8 +1023,8 @@ static int launch_bwd_vec_impl(const Problem& pr, const void* value, const int64
   ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD, st);
   msda_bwd_vec_kernel<T, D, false, FUSED, AT><<<grid, kThreads, smem, st>>>(
       static_cast<const T*>(value), shapes, lsi, static_cast<const AT*>(loc), static_cast<const AT*>(attn),
-      pr.ref, pr.R, static_cast<const T*>(go), gv32, nullptr, nullptr, static_cast<AT*>(gloc), static_cast<AT*>(gattn),
-      pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth);
+      pr.ref, pr.R, static_cast<const T*>(go), gv32, nullptr, nullptr, nullptr, static_cast<AT*>(gloc), static_cast<AT*>(gattn),
+      pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth, pr.value_stride(), gv_stride);
   ++g_last_launches, ++g_total_launches;
   return static_cast<int>(cudaGetLastError());
 }
@@ -978,14 +1032,15 @@ static int launch_bwd_vec_impl(const Problem& pr, const void* value, const int64
 template <typename T, int D>
 static int launch_bwd_vec(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
                           const void* loc, const void* attn, const void* go, float* gv32, __half* gv16,
+                          void* gvd, int gvs,
                           const uint32_t* ctrl, void* gloc, void* gattn, bool use16, int depth, cudaStream_t st) {
   if constexpr (sizeof(T) == 2) {
     if (pr.ref && pr.aux16)
-      return launch_bwd_vec_impl<T, D, true, T>(pr, value, shapes, lsi, loc, attn, go, gv32, gv16, ctrl, gloc, gattn, use16, depth, st);
+      return launch_bwd_vec_impl<T, D, true, T>(pr, value, shapes, lsi, loc, attn, go, gv32, gv16, gvd, gvs, ctrl, gloc, gattn, use16, depth, st);
   }
   if (pr.ref)
-    return launch_bwd_vec_impl<T, D, true, float>(pr, value, shapes, lsi, loc, attn, go, gv32, gv16, ctrl, gloc, gattn, use16, depth, st);
-  return launch_bwd_vec_impl<T, D, false, float>(pr, value, shapes, lsi, loc, attn, go, gv32, gv16, ctrl, gloc, gattn, use16, depth, st);
+    return launch_bwd_vec_impl<T, D, true, float>(pr, value, shapes, lsi, loc, attn, go, gv32, gv16, gvd, gvs, ctrl, gloc, gattn, use16, depth, st);
+  return launch_bwd_vec_impl<T, D, false, float>(pr, value, shapes, lsi, loc, attn, go, gv32, gv16, gvd, gvs, ctrl, gloc, gattn, use16, depth, st);
 }
 
 template <typename T>
@@ -996,16 +1051,25 @@ MSDA_LAUNCHER int launch_bwd(const Problem& pr, const void* value, const int64_t
   constexpr bool k16 = sizeof(T) == 2;
   const bool use16 = k16 && !(flags & MSDA_BWD_GRAD_VALUE_FP32_ACCUM) && vec_supported<T>(pr);
   const int depth = accum_depth(flags);
+  const bool sparse_direct = use16 && !(flags & MSDA_BWD_NO_SPARSE_DIRECT);
+  // strided grad_value: the vector kernels with direct (fp32 / fp64-free) or fp16-bucket accumulation only
+  if (pr.strided() && (!vec_supported<T>(pr) || std::is_same<T, double>::value || (k16 && !use16))) return MSDA_ERR_BAD_STRIDE;
+  const int gstride = pr.grad_stride();
   // 16-bit values accumulate in the scratch and grad_value is fully overwritten by the rounding pass, so only
   // the buffer that receives the reductions is zeroed
   cudaError_t e;
   uint32_t* ctrl = nullptr;
   __half* acc16 = nullptr;
   if (!k16) {
-    e = cudaMemsetAsync(gv, 0, n_value * sizeof(T), st);
+    if (gstride == pr.M * pr.D)
+      e = cudaMemsetAsync(gv, 0, n_value * sizeof(T), st);
+    else
+      e = cudaMemset2DAsync(gv, static_cast<size_t>(gstride) * sizeof(T), 0, static_cast<size_t>(pr.M) * pr.D * sizeof(T),
+                            static_cast<size_t>(pr.N) * pr.S, st);
   } else if (use16) {
     msda_zero_f16_buckets_kernel<<<148 * 8, 256, 0, st>>>(static_cast<uint4*>(scratch), kF16CtrlBytes / 16, shapes, lsi,
-                                                         pr.N, pr.M, pr.D, pr.Lq, pr.L, pr.P, depth);
+                                                         sparse_direct ? static_cast<uint16_t*>(gv) : nullptr,
+                                                         pr.N, pr.S, pr.M, pr.D, pr.Lq, pr.L, pr.P, depth, gstride);
     ++g_last_launches, ++g_total_launches;
     e = cudaGetLastError();
     ctrl = static_cast<uint32_t*>(scratch);
@@ -1029,11 +1093,13 @@ MSDA_LAUNCHER int launch_bwd(const Problem& pr, const void* value, const int64_t
   if constexpr (!std::is_same<T, double>::value) {
     if (vec_supported<T>(pr)) {
       float* gv32 = k16 ? static_cast<float*>(scratch) : static_cast<float*>(gv);
+      void* gvd = sparse_direct ? gv : nullptr;                      // sparse levels add straight into grad_value
+      const int gvs = (k16 && !use16) ? pr.M * pr.D : gstride;       // the fp32 scratch of 16-bit values is dense
       switch (pr.D) {
-        case 16: rc = launch_bwd_vec<T, 16>(pr, value, shapes, lsi, loc, attn, go, gv32, acc16, ctrl, gloc, gattn, use16, depth, st); break;
-        case 32: rc = launch_bwd_vec<T, 32>(pr, value, shapes, lsi, loc, attn, go, gv32, acc16, ctrl, gloc, gattn, use16, depth, st); break;
-        case 64: rc = launch_bwd_vec<T, 64>(pr, value, shapes, lsi, loc, attn, go, gv32, acc16, ctrl, gloc, gattn, use16, depth, st); break;
-        default: rc = launch_bwd_vec<T, 128>(pr, value, shapes, lsi, loc, attn, go, gv32, acc16, ctrl, gloc, gattn, use16, depth, st); break;
+        case 16: rc = launch_bwd_vec<T, 16>(pr, value, shapes, lsi, loc, attn, go, gv32, acc16, gvd, gvs, ctrl, gloc, gattn, use16, depth, st); break;
+        case 32: rc = launch_bwd_vec<T, 32>(pr, value, shapes, lsi, loc, attn, go, gv32, acc16, gvd, gvs, ctrl, gloc, gattn, use16, depth, st); break;
+        case 64: rc = launch_bwd_vec<T, 64>(pr, value, shapes, lsi, loc, attn, go, gv32, acc16, gvd, gvs, ctrl, gloc, gattn, use16, depth, st); break;
+        default: rc = launch_bwd_vec<T, 128>(pr, value, shapes, lsi, loc, attn, go, gv32, acc16, gvd, gvs, ctrl, gloc, gattn, use16, depth, st); break;
       }
       done = true;
     }
@@ -1062,7 +1128,8 @@ MSDA_LAUNCHER int launch_bwd(const Problem& pr, const void* value, const int64_t
       const size_t n8 = n_value / 8;
       const int grid = static_cast<int>(std::min<size_t>((n8 + 255) / 256, 148 * 16));
       msda_round_f16_buckets_kernel<T><<<grid, 256, 0, st>>>(acc16, static_cast<T*>(gv), shapes, lsi, ctrl, pr.N, pr.S,
-                                                            pr.M, pr.D, pr.Lq, pr.L, pr.P, depth);
+                                                            pr.M, pr.D, pr.Lq, pr.L, pr.P, depth, sparse_direct ? 1 : 0,
+                                                            gstride);
       ++g_last_launches, ++g_total_launches;
       rc = static_cast<int>(cudaGetLastError());
     } else {
@@ -1110,7 +1177,7 @@ MSDA_LAUNCHERS_OF(, __half)
 // =====================================================================================================
 using namespace msda;
 
-extern "C" int msda_abi_version(void) { return 3; }
+extern "C" int msda_abi_version(void) { return 4; }
 
 extern "C" const char* msda_error_string(int code) {
   switch (code) {
@@ -1121,6 +1188,9 @@ extern "C" const char* msda_error_string(int code) {
     case MSDA_ERR_MISALIGNED: return "buffer is not 16-byte aligned";
     case MSDA_ERR_IM2COL_STEP: return "batch size must be divisible by min(batch, im2col_step)";
     case MSDA_ERR_SCRATCH_TOO_SMALL: return "scratch buffer missing or too small";
+    case MSDA_ERR_BAD_STRIDE:
+      return "pixel stride must be >= M*D elements and a multiple of 16 bytes; strided tensors need the vector kernels "
+             "(head dim 16/32/64/128, not float64) and, for 16-bit values, the default accumulation mode";
     case MSDA_ERR_FUSED_UNSUPPORTED:
       return "fused pre-op needs float32/bfloat16/float16 values with head dim 16/32/64/128 and reference points of width 2 or 4";
     default: break;
@@ -1153,14 +1223,22 @@ extern "C" int msda_profile_collect(float* ms, int* kinds, int max_records) {
   return n;
 }
 
-extern "C" int msda_forward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                            const void* sampling_loc, const void* attn_weight, void* output,
-                            int N, int S, int M, int D, int Lq, int L, int P,
-                            int value_dtype, int im2col_step, void* stream) {
+static size_t dtype_bytes(int value_dtype) {
+  return value_dtype == MSDA_F64 ? 8 : value_dtype == MSDA_F32 ? 4 : 2;
+}
+
+extern "C" int msda_forward_strided(const void* value, long long value_pixel_stride,
+                                    const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                    const void* sampling_loc, const void* attn_weight, void* output,
+                                    int N, int S, int M, int D, int Lq, int L, int P,
+                                    int value_dtype, int im2col_step, void* stream) {
   g_last_launches = 0;
   if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !output) return MSDA_ERR_NULL_POINTER;
   Problem pr{N, S, M, D, Lq, L, P, 0};
-  const int v = validate(pr, value_dtype, im2col_step);
+  int v = validate(pr, value_dtype, im2col_step);
+  if (v != MSDA_OK) return v;
+  pr.vps = value_pixel_stride;
+  v = validate_strides(pr, dtype_bytes(value_dtype));
   if (v != MSDA_OK) return v;
   pr.total_pairs = N * Lq * M;
   if (!aligned16(value) || !aligned16(sampling_loc) || !aligned16(attn_weight) || !aligned16(output)) return MSDA_ERR_MISALIGNED;
@@ -1172,6 +1250,14 @@ extern "C" int msda_forward(const void* value, const int64_t* spatial_shapes, co
     case MSDA_F16: return launch_fwd<__half>(pr, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, st);
   }
   return MSDA_ERR_BAD_DTYPE;
+}
+
+extern "C" int msda_forward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                            const void* sampling_loc, const void* attn_weight, void* output,
+                            int N, int S, int M, int D, int Lq, int L, int P,
+                            int value_dtype, int im2col_step, void* stream) {
+  return msda_forward_strided(value, 0, spatial_shapes, level_start_index, sampling_loc, attn_weight, output,
+                              N, S, M, D, Lq, L, P, value_dtype, im2col_step, stream);
 }
 
 extern "C" size_t msda_backward_scratch_bytes(int N, int S, int M, int D, int Lq, int L, int P, int value_dtype, int flags) {
@@ -1189,12 +1275,29 @@ extern "C" int msda_backward(const void* value, const int64_t* spatial_shapes, c
                              void* scratch, size_t scratch_bytes,
                              int N, int S, int M, int D, int Lq, int L, int P,
                              int value_dtype, int im2col_step, int flags, void* stream) {
+  return msda_backward_strided(value, 0, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                               grad_value, 0, grad_sampling_loc, grad_attn_weight, scratch, scratch_bytes,
+                               N, S, M, D, Lq, L, P, value_dtype, im2col_step, flags, stream);
+}
+
+extern "C" int msda_backward_strided(const void* value, long long value_pixel_stride,
+                                     const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                     const void* sampling_loc, const void* attn_weight, const void* grad_output,
+                                     void* grad_value, long long grad_value_pixel_stride,
+                                     void* grad_sampling_loc, void* grad_attn_weight,
+                                     void* scratch, size_t scratch_bytes,
+                                     int N, int S, int M, int D, int Lq, int L, int P,
+                                     int value_dtype, int im2col_step, int flags, void* stream) {
   g_last_launches = 0;
   if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_output ||
       !grad_value || !grad_sampling_loc || !grad_attn_weight)
     return MSDA_ERR_NULL_POINTER;
   Problem pr{N, S, M, D, Lq, L, P, 0};
-  const int v = validate(pr, value_dtype, im2col_step);
+  int v = validate(pr, value_dtype, im2col_step);
+  if (v != MSDA_OK) return v;
+  pr.vps = value_pixel_stride;
+  pr.gps = grad_value_pixel_stride;
+  v = validate_strides(pr, dtype_bytes(value_dtype));
   if (v != MSDA_OK) return v;
   pr.total_pairs = N * Lq * M;
   if (!aligned16(value) || !aligned16(sampling_loc) || !aligned16(attn_weight) || !aligned16(grad_output) ||

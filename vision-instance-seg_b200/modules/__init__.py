@@ -1,3 +1,4 @@
 from .ms_deform_attn import MSDeformAttn, set_fused_preop  # noqa: F401
 from .encoder import (MSDeformAttnTransformerEncoder, MSDeformAttnTransformerEncoderLayer,  # noqa: F401
                       MSDeformAttnTransformerEncoderOnly, set_fused_encoder_layers)
+from .stacked_value_proj import StackedValueProj, share_value_proj, unshare_value_proj  # noqa: F401

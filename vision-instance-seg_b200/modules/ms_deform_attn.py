@@ -21,6 +21,7 @@ from torch.nn.init import constant_, xavier_uniform_
 
 from .. import MultiScaleDeformableAttention as MSDA
 from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
+from .stacked_value_proj import MSDeformAttnStackedFunction
 
 
 def _is_power_of_2(n):
@@ -45,6 +46,9 @@ class MSDeformAttn(nn.Module):
     #: materialising ``sampling_locations`` / ``attention_weights`` (same maths and rounding order; no new parameters,
     #: so checkpoints are unaffected).  Constructor signature stays upstream's; flip it with ``set_fused_preop``.
     fused_preop = False
+    #: opt-in: (StackedValueProj, index) when this module shares one stacked ``value_proj`` GEMM with the other decoder
+    #: layers' cross-attention modules (see modules/stacked_value_proj.py ``share_value_proj``)
+    _stacked_value = None
 
     def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
         """Multi-Scale Deformable Attention Module
@@ -110,10 +114,16 @@ class MSDeformAttn(nn.Module):
         N, Len_in, _ = input_flatten.shape
         assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
 
-        value = self.value_proj(input_flatten)
-        if input_padding_mask is not None:
-            value = value.masked_fill(input_padding_mask[..., None], float(0))
-        value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+        stacked = None
+        if self._stacked_value is not None and input_flatten.is_cuda:
+            proj, index = self._stacked_value
+            stacked = proj.value_for(index, input_flatten, input_padding_mask)   # (view, value_all, grad state)
+            value = stacked[0]
+        else:
+            value = self.value_proj(input_flatten)
+            if input_padding_mask is not None:
+                value = value.masked_fill(input_padding_mask[..., None], float(0))
+            value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         sampling_offsets = self.sampling_offsets(query) \
             .view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
         attention_weights = self.attention_weights(query) \
@@ -121,7 +131,7 @@ class MSDeformAttn(nn.Module):
         if reference_points.shape[-1] not in (2, 4):
             raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead."
                              .format(reference_points.shape[-1]))
-        if self.fused_preop and MSDA.fused_supported(value, reference_points) \
+        if stacked is None and self.fused_preop and MSDA.fused_supported(value, reference_points) \
                 and not (torch.is_grad_enabled() and reference_points.requires_grad):
             output = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index,
                                                      reference_points.contiguous(), sampling_offsets.contiguous(),
@@ -139,6 +149,12 @@ class MSDeformAttn(nn.Module):
         else:
             raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead."
                              .format(reference_points.shape[-1]))
+        if stacked is not None:
+            output = MSDeformAttnStackedFunction.apply(value, stacked[1], stacked[2], self._stacked_value[1],
+                                                       input_spatial_shapes, input_level_start_index,
+                                                       sampling_locations.contiguous(), attention_weights.contiguous(),
+                                                       self.im2col_step)
+            return self.output_proj(output)
         output = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index,
                                             sampling_locations, attention_weights, self.im2col_step)
         output = self.output_proj(output)
