@@ -230,3 +230,58 @@ def test_shared_value_proj_partial_use_and_double_use(ops):
                 assert b is None or float(b.abs().max()) == 0.0
             else:
                 assert rel_to_max(b, a) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------
+# decoder harness end to end (box reference points, the same memory for every layer)
+# ---------------------------------------------------------------------------------------------------
+class _OracleFunction:
+    @staticmethod
+    def apply(value, shapes, lsi, loc, attn, im2col_step):
+        from oracle import ms_deform_attn_core_pytorch
+        return ms_deform_attn_core_pytorch(value, shapes, loc, attn)
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_decoder_matches_cpu_restatement(ops, monkeypatch, shared):
+    import copy
+    from vision_instance_seg_b200.modules import build_decoder, set_shared_value_proj
+    from vision_instance_seg_b200.modules import ms_deform_attn as MOD
+    torch.manual_seed(11)
+    dec_cpu = build_decoder(d_model=64, nhead=4, num_decoder_layers=3, dim_feedforward=128, num_feature_levels=3)
+    with torch.no_grad():
+        for layer in dec_cpu.layers:
+            layer.cross_attn.sampling_offsets.weight.normal_(0, 0.05)
+            layer.cross_attn.attention_weights.weight.normal_(0, 0.3)
+    dec_gpu = copy.deepcopy(dec_cpu).cuda()
+    if shared:
+        set_shared_value_proj(dec_gpu)
+    shapes = [(12, 20), (6, 10), (3, 5)]
+    ss = torch.as_tensor(shapes, dtype=torch.long)
+    lsi = lsi_of(ss)
+    S, N, Lq = int(ss.prod(1).sum()), 2, 17
+    g = torch.Generator().manual_seed(5)
+    memory = torch.randn(S, N, 64, generator=g)
+    tgt = torch.randn(Lq, N, 64, generator=g)
+    refs = torch.randn(Lq, N, 4, generator=g)
+    mask = torch.rand(N, S, generator=g) < 0.15
+    vr = torch.rand(N, 3, 2, generator=g) * 0.3 + 0.7
+
+    monkeypatch.setattr(MOD, "MSDeformAttnFunction", _OracleFunction)
+    mem_c = memory.clone().requires_grad_(True)
+    outs_c, _ = dec_cpu(tgt, mem_c, memory_key_padding_mask=mask, refpoints_unsigmoid=refs, level_start_index=lsi,
+                        spatial_shapes=ss, valid_ratios=vr)
+    gout = torch.randn_like(outs_c[-1])
+    (outs_c[-1] * gout + outs_c[0] * 0.5).sum().backward()
+    monkeypatch.undo()
+
+    mem_g = memory.cuda().requires_grad_(True)
+    outs_g, _ = dec_gpu(tgt.cuda(), mem_g, memory_key_padding_mask=mask.cuda(), refpoints_unsigmoid=refs.cuda(),
+                        level_start_index=lsi.cuda(), spatial_shapes=ss.cuda(), valid_ratios=vr.cuda())
+    (outs_g[-1] * gout.cuda() + outs_g[0] * 0.5).sum().backward()
+    torch.cuda.synchronize()
+    for a, b in zip(outs_g, outs_c):
+        assert rel_to_max(a, b) < 1e-4
+    assert rel_to_max(mem_g.grad, mem_c.grad) < 2e-4
+    for (name, pg), (_, pc) in zip(dec_gpu.named_parameters(), dec_cpu.named_parameters()):
+        assert rel_to_max(pg.grad, pc.grad) < 5e-4, name

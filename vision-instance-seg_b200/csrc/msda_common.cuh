@@ -98,6 +98,8 @@ struct LevelMeta {
   int accStride;             // pixel rows per image of the accumulator
   int dirOff[kMaxLevels];    // sparse levels: first row of the level among one image's directly accumulated rows
   int dirRows;               // directly accumulated pixel rows per image
+  int bktOff[kMaxLevels];    // bucketed levels: first row of the level among one image's bucketed pixel rows
+  int bktRows;               // bucketed pixel rows per image (dirRows + bktRows = S)
 };
 
 __device__ __forceinline__ void load_level_meta(LevelMeta& meta, const int64_t* __restrict__ shapes,
@@ -135,7 +137,7 @@ __host__ __device__ inline long long accum_rows_bound(int S, int L, int Lq, int 
 // call after load_level_meta (thread 0 fills, then a barrier)
 __device__ __forceinline__ void build_accum_layout(LevelMeta& meta, int L, int Lq, int P, int depth, bool sparse_direct) {
   if (threadIdx.x == 0) {
-    int base = 0, dir = 0;
+    int base = 0, dir = 0, bkt = 0;
     for (int l = 0; l < L; ++l) {
       const long long hw = static_cast<long long>(meta.H[l]) * meta.W[l];
       const long long adds = hw > 0 ? (static_cast<long long>(Lq) * P + hw - 1) / hw : 1;
@@ -144,11 +146,13 @@ __device__ __forceinline__ void build_accum_layout(LevelMeta& meta, int L, int L
       meta.accK[l] = direct ? 0 : (K < 1 ? 1 : K);
       meta.accBase[l] = base;
       meta.dirOff[l] = dir;
+      meta.bktOff[l] = bkt;
       base += meta.accK[l] * static_cast<int>(hw);
-      if (direct) dir += static_cast<int>(hw);
+      if (direct) dir += static_cast<int>(hw); else bkt += static_cast<int>(hw);
     }
     meta.accStride = base;
     meta.dirRows = dir;
+    meta.bktRows = bkt;
   }
   __syncthreads();
 }

@@ -669,16 +669,20 @@ msda_round_f16_buckets_kernel(const __half* __restrict__ acc, T* __restrict__ ds
   build_accum_layout(meta, L, Lq, P, depth, sparse_direct != 0);
   const float inv = 1.f / f16_accum_scale(ctrl, Lq);        // exact: power of two
   const int vec_per_pix = M * D / 8;
-  const size_t total = static_cast<size_t>(N) * S * vec_per_pix;
+  // only the bucketed levels' rows are visited: a sparse level's grad_value rows already hold their sums
+  const size_t per_img = static_cast<size_t>(meta.bktRows) * vec_per_pix;
+  const size_t total = static_cast<size_t>(N) * per_img;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const size_t pix = i / vec_per_pix;
-    const int v = static_cast<int>(i - pix * vec_per_pix);
-    const int b = static_cast<int>(pix / S);
-    const int s = static_cast<int>(pix - static_cast<size_t>(b) * S);
+    const int b = static_cast<int>(i / per_img);
+    const size_t rem = i - static_cast<size_t>(b) * per_img;
+    const int r = static_cast<int>(rem / vec_per_pix);               // row among the image's bucketed rows
+    const int v = static_cast<int>(rem - static_cast<size_t>(r) * vec_per_pix);
     int l = 0;
-    while (l + 1 < L && s >= meta.start[l + 1]) ++l;
-    if (meta.accK[l] == 0) continue;      // sparse level: grad_value already holds the sums
+    for (int k = 0; k < L; ++k)
+      if (meta.accK[k] != 0 && r >= meta.bktOff[k]) l = k;
+    const int s = meta.start[l] + (r - meta.bktOff[l]);
+    const size_t pix = static_cast<size_t>(b) * S + s;
     const int hw = meta.H[l] * meta.W[l];
     const size_t row0 = static_cast<size_t>(b) * meta.accStride + meta.accBase[l] + (s - meta.start[l]);
     float sum[8];
