@@ -376,7 +376,10 @@ __device__ __forceinline__ float f16_accum_scale(const uint32_t* __restrict__ ct
 // FUSED   : `loc` / `attn` hold raw sampling offsets / attention logits, `ref` (N, Lq, L, R) the reference points;
 //           `grad_loc` / `grad_attn` receive the gradients of the raw offsets / logits (see fused_prepare).
 // AT      : element type of `loc` / `attn` / `grad_loc` / `grad_attn` (float; fused kernels also the 16-bit value type)
-template <typename T, int D, bool GV16, bool FUSED, typename AT>
+// SPARSE  : GV16 only; some level may be sparse (2*Lq*P <= H_l*W_l <= S, decided on the host from Lq, P, S) and then
+//           adds straight into grad_value (build_accum_layout).  A separate instantiation because the extra
+//           level-uniform branch and addressing in the reduction loop cost the dense encoder shapes ~8 %.
+template <typename T, int D, bool GV16, bool FUSED, typename AT, bool SPARSE>
 __global__ void __launch_bounds__(kThreads, BWD_MIN_CTAS)
 msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const AT* __restrict__ loc,
@@ -398,7 +401,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   extern __shared__ __align__(16) float smem[];
   __shared__ LevelMeta meta;
   load_level_meta(meta, shapes, lsi, L);
-  if constexpr (GV16) build_accum_layout(meta, L, Lq, P, depth, gv_direct != nullptr);
+  if constexpr (GV16) build_accum_layout(meta, L, Lq, P, depth, SPARSE);
 
   const int LP = L * P;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -468,14 +471,17 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   float gv_unscale = 1.f;
   if constexpr (GV16) {
     gv16_base = gv16 + (static_cast<size_t>(b) * meta.accStride * M + m) * D + c * VEC;
-    gvd_base = gv_direct + (static_cast<size_t>(b) * S * gps + m * D) + c * VEC;
-    direct = meta.accK[0] == 0;
+    if constexpr (SPARSE) {
+      gvd_base = gv_direct + (static_cast<size_t>(b) * S * gps + m * D) + c * VEC;
+      direct = meta.accK[0] == 0;
+    }
     acc_row = static_cast<size_t>(meta.accBase[0]) + static_cast<size_t>(direct ? 0 : q % meta.accK[0]) * (meta.H[0] * meta.W[0]);
     gv_unscale = 1.f / gv_scale;          // exact: power of two
 #pragma unroll
     for (int i = 0; i < VEC; ++i) go_s[i] *= gv_scale;      // exact: power-of-two scale
   }
   const uint32_t pix_elems = static_cast<uint32_t>(M) * D;
+  const uint32_t gps_elems = static_cast<uint32_t>(gps);
 
   // Points are processed in chunks of CH; groups of up to 8 lanes reduce-scatter a chunk of G points at once,
   // wider groups (D = 64 fp32, D = 128) fall back to one butterfly per point to keep registers in check.
@@ -508,22 +514,23 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (w[k] != 0.f) {            // invalid corners (and exact-zero weights) add nothing
-              const size_t e = (lvl_pix + idx[k]) * static_cast<size_t>(gps);
               float r[VEC];
 #pragma unroll
               for (int i = 0; i < VEC; ++i) r[i] = w[k] * go_s[i];
               if constexpr (GV16) {
-                if (direct) {             // sparse level: unscaled, in the value dtype, into grad_value
+                if (SPARSE && direct) {   // sparse level: unscaled, in the value dtype, into grad_value
 #pragma unroll
                   for (int i = 0; i < VEC; ++i) r[i] *= gv_unscale;
-                  red_add_16bit_x8<T>(gvd_base + e, pack16<T>(r));
+                  red_add_16bit_x8<T>(gvd_base + (lvl_pix + idx[k]) * gps_elems, pack16<T>(r));
                 } else {
                   red_add_16bit_x8<__half>(gv16_base + (acc_row + idx[k]) * pix_elems, pack16<__half>(r));
                 }
               } else if constexpr (k16) {
+                const size_t e = (lvl_pix + idx[k]) * gps_elems;
                 red_add_f32x4(gv32_base + e, r[0], r[1], r[2], r[3]);
                 red_add_f32x4(gv32_base + e + D / 2, r[4], r[5], r[6], r[7]);
               } else {
+                const size_t e = (lvl_pix + idx[k]) * gps_elems;
                 red_add_f32x4(gv32_base + e, r[0], r[1], r[2], r[3]);
               }
             }
@@ -542,7 +549,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
             H = meta.H[l]; W = meta.W[l]; Hf = static_cast<float>(H); Wf = static_cast<float>(W);
             lvl_pix = static_cast<size_t>(meta.start[l]);
             if constexpr (GV16) {
-              direct = meta.accK[l] == 0;
+              if constexpr (SPARSE) direct = meta.accK[l] == 0;
               acc_row = static_cast<size_t>(meta.accBase[l]) + static_cast<size_t>(direct ? 0 : q % meta.accK[l]) * (H * W);
             }
           }
@@ -668,16 +675,14 @@ msda_round_f16_buckets_kernel(const __half* __restrict__ acc, T* __restrict__ ds
   load_level_meta(meta, shapes, lsi, L);
   build_accum_layout(meta, L, Lq, P, depth, sparse_direct != 0);
   const float inv = 1.f / f16_accum_scale(ctrl, Lq);        // exact: power of two
-  const int vec_per_pix = M * D / 8;
-  // only the bucketed levels' rows are visited: a sparse level's grad_value rows already hold their sums
-  const size_t per_img = static_cast<size_t>(meta.bktRows) * vec_per_pix;
-  const size_t total = static_cast<size_t>(N) * per_img;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int b = static_cast<int>(i / per_img);
-    const size_t rem = i - static_cast<size_t>(b) * per_img;
-    const int r = static_cast<int>(rem / vec_per_pix);               // row among the image's bucketed rows
-    const int v = static_cast<int>(rem - static_cast<size_t>(r) * vec_per_pix);
+  const uint32_t vec_per_pix = static_cast<uint32_t>(M * D / 8);
+  // blockIdx.y = image; only the bucketed levels' rows are visited (a sparse level's grad_value rows already hold
+  // their sums); 32-bit index arithmetic (S * M * D * 4 bytes < 2^32 for the vector kernels)
+  const uint32_t per_img = static_cast<uint32_t>(meta.bktRows) * vec_per_pix;
+  for (int b = blockIdx.y; b < N; b += gridDim.y)
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per_img; i += gridDim.x * blockDim.x) {
+    const int r = static_cast<int>(i / vec_per_pix);                 // row among the image's bucketed rows
+    const int v = static_cast<int>(i - static_cast<uint32_t>(r) * vec_per_pix);
     int l = 0;
     for (int k = 0; k < L; ++k)
       if (meta.accK[k] != 0 && r >= meta.bktOff[k]) l = k;
@@ -1011,21 +1016,25 @@ static int launch_bwd_vec_impl(const Problem& pr, const void* value, const int64
   cudaError_t e;
   if constexpr (sizeof(T) == 2) {
     if (use16) {
-      e = allow_smem(msda_bwd_vec_kernel<T, D, true, FUSED, AT>, smem);
-      if (e != cudaSuccess) return static_cast<int>(e);
-      ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD, st);
-      msda_bwd_vec_kernel<T, D, true, FUSED, AT><<<grid, kThreads, smem, st>>>(
-          static_cast<const T*>(value), shapes, lsi, static_cast<const AT*>(loc), static_cast<const AT*>(attn),
-          pr.ref, pr.R, static_cast<const T*>(go), nullptr, gv16, static_cast<T*>(gv_direct), ctrl, static_cast<AT*>(gloc),
-          static_cast<AT*>(gattn), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth, pr.value_stride(), gv_stride);
-      ++g_last_launches, ++g_total_launches;
-      return static_cast<int>(cudaGetLastError());
+      auto launch16 = [&](auto kernel) -> int {
+        cudaError_t err = allow_smem(kernel, smem);
+        if (err != cudaSuccess) return static_cast<int>(err);
+        ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD, st);
+        kernel<<<grid, kThreads, smem, st>>>(
+            static_cast<const T*>(value), shapes, lsi, static_cast<const AT*>(loc), static_cast<const AT*>(attn),
+            pr.ref, pr.R, static_cast<const T*>(go), nullptr, gv16, static_cast<T*>(gv_direct), ctrl, static_cast<AT*>(gloc),
+            static_cast<AT*>(gattn), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth, pr.value_stride(), gv_stride);
+        ++g_last_launches, ++g_total_launches;
+        return static_cast<int>(cudaGetLastError());
+      };
+      return gv_direct ? launch16(msda_bwd_vec_kernel<T, D, true, FUSED, AT, true>)
+                       : launch16(msda_bwd_vec_kernel<T, D, true, FUSED, AT, false>);
     }
   }
-  e = allow_smem(msda_bwd_vec_kernel<T, D, false, FUSED, AT>, smem);
+  e = allow_smem(msda_bwd_vec_kernel<T, D, false, FUSED, AT, false>, smem);
   if (e != cudaSuccess) return static_cast<int>(e);
   ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD, st);
-  msda_bwd_vec_kernel<T, D, false, FUSED, AT><<<grid, kThreads, smem, st>>>(
+  msda_bwd_vec_kernel<T, D, false, FUSED, AT, false><<<grid, kThreads, smem, st>>>(
       static_cast<const T*>(value), shapes, lsi, static_cast<const AT*>(loc), static_cast<const AT*>(attn),
       pr.ref, pr.R, static_cast<const T*>(go), gv32, nullptr, nullptr, nullptr, static_cast<AT*>(gloc), static_cast<AT*>(gattn),
       pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth, pr.value_stride(), gv_stride);
@@ -1055,7 +1064,8 @@ MSDA_LAUNCHER int launch_bwd(const Problem& pr, const void* value, const int64_t
   constexpr bool k16 = sizeof(T) == 2;
   const bool use16 = k16 && !(flags & MSDA_BWD_GRAD_VALUE_FP32_ACCUM) && vec_supported<T>(pr);
   const int depth = accum_depth(flags);
-  const bool sparse_direct = use16 && !(flags & MSDA_BWD_NO_SPARSE_DIRECT);
+  // a level can only be sparse (2*Lq*P <= H_l*W_l) if 2*Lq*P <= S: decided here, the levels themselves on the device
+  const bool sparse_direct = use16 && !(flags & MSDA_BWD_NO_SPARSE_DIRECT) && 2ll * pr.Lq * pr.P <= pr.S;
   // strided grad_value: the vector kernels with direct (fp32 / fp64-free) or fp16-bucket accumulation only
   if (pr.strided() && (!vec_supported<T>(pr) || std::is_same<T, double>::value || (k16 && !use16))) return MSDA_ERR_BAD_STRIDE;
   const int gstride = pr.grad_stride();
@@ -1129,8 +1139,9 @@ MSDA_LAUNCHER int launch_bwd(const Problem& pr, const void* value, const int64_t
   if (rc != 0) return rc;
   if constexpr (k16) {
     if (use16) {
-      const size_t n8 = n_value / 8;
-      const int grid = static_cast<int>(std::min<size_t>((n8 + 255) / 256, 148 * 16));
+      const size_t n8_img = static_cast<size_t>(pr.S) * pr.M * pr.D / 8;
+      const size_t want = (n8_img + 255) / 256, cap = std::max<size_t>(1, (148 * 16) / static_cast<size_t>(pr.N));
+      const dim3 grid(static_cast<unsigned>(std::min(want, cap)), static_cast<unsigned>(std::min(pr.N, 65535)));
       msda_round_f16_buckets_kernel<T><<<grid, 256, 0, st>>>(acc16, static_cast<T*>(gv), shapes, lsi, ctrl, pr.N, pr.S,
                                                             pr.M, pr.D, pr.Lq, pr.L, pr.P, depth, sparse_direct ? 1 : 0,
                                                             gstride);
