@@ -55,6 +55,8 @@ def parse_args():
                     help="train-step workloads: capture forward + backward + all-reduce + optimizer in one CUDA graph")
     ap.add_argument("--fused-layers", action="store_true",
                     help="train-step workloads: run every encoder layer as one fused autograd node (implies --fused-preop)")
+    ap.add_argument("--shared-value-proj", action="store_true",
+                    help="decoder-step workload: one stacked value_proj GEMM for all decoder layers (share_value_proj)")
     return ap.parse_args()
 
 
@@ -391,23 +393,70 @@ def run_train_step(args):
     S = sum(h * w for h, w in shapes)
 
     torch.manual_seed(1234)                     # identical parameters on every rank
-    enc = MSDeformAttnTransformerEncoderOnly(d_model=C, nhead=M, num_encoder_layers=layers, dim_feedforward=cfg["d_ffn"],
-                                             dropout=0.0, num_feature_levels=L, enc_n_points=P).to(dev)
-    with torch.no_grad():                       # trained-like projections: offsets / weights depend on the query
-        for layer in enc.encoder.layers:
-            layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
-            layer.self_attn.attention_weights.weight.normal_(0, 0.05)
-    pkg.set_fused_preop(enc, args.fused_preop)
-    pkg.set_fused_encoder_layers(enc, args.fused_layers)
-    buckets = D.GradientBuckets(D.encoder_gradient_groups(enc), device=dev)
+    decoder_step = cfg["kind"] == "decoder_step"
+    if decoder_step:
+        # BASELINE configs[3]: the deformable decoder (9 layers, `queries` box queries) on a fixed encoder memory; the
+        # memory is a differentiable input (its gradient is what the encoder would receive), every layer's output is
+        # supervised (DETR-style auxiliary losses)
+        from vision_instance_seg_b200.modules.decoder import build_decoder, set_shared_value_proj
+        Lq = cfg["queries"]
+        enc = build_decoder(d_model=C, nhead=M, num_decoder_layers=layers, dim_feedforward=cfg["d_ffn"], dropout=0.0,
+                            num_feature_levels=L, dec_n_points=P).to(dev)
+        with torch.no_grad():
+            for layer in enc.layers:
+                layer.cross_attn.sampling_offsets.weight.normal_(0, 0.01)
+                layer.cross_attn.attention_weights.weight.normal_(0, 0.05)
+        if args.shared_value_proj:
+            set_shared_value_proj(enc)
+        pkg.set_fused_preop(enc, args.fused_preop)
+        groups = [list(layer.parameters()) for layer in reversed(list(enc.layers))]
+        groups.append(list(enc.ref_point_head.parameters()) + list(enc.norm.parameters()))
+        buckets = D.GradientBuckets(groups, device=dev)
+        gen = torch.Generator().manual_seed(99 + start)
+        host_srcs = [torch.randn(S, count, C, generator=gen).pin_memory()]           # encoder memory, sequence first
+        tgt = torch.randn(Lq, count, C, generator=gen).to(dev)
+        refs = torch.randn(Lq, count, 4, generator=gen).to(dev)
+        ss_dev = W.make_spatial_shapes(shapes, dev)
+        lsi_dev = W.make_level_start_index(ss_dev)
+        vr = torch.ones(count, L, 2, device=dev)
+        pos = None
+        pts_per_step = global_batch * Lq * M * L * P * layers
+    else:
+        enc = MSDeformAttnTransformerEncoderOnly(d_model=C, nhead=M, num_encoder_layers=layers, dim_feedforward=cfg["d_ffn"],
+                                                 dropout=0.0, num_feature_levels=L, enc_n_points=P).to(dev)
+        with torch.no_grad():                       # trained-like projections: offsets / weights depend on the query
+            for layer in enc.encoder.layers:
+                layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
+                layer.self_attn.attention_weights.weight.normal_(0, 0.05)
+        pkg.set_fused_preop(enc, args.fused_preop)
+        pkg.set_fused_encoder_layers(enc, args.fused_layers)
+        buckets = D.GradientBuckets(D.encoder_gradient_groups(enc), device=dev)
+        host_srcs, host_pos = W.make_feature_pyramid(shapes, count, C, seed=99 + start, device="cpu", pin=True)
+        pos = [t.to(dev) for t in host_pos]
+        pts_per_step = global_batch * S * M * L * P * layers
     opt = torch.optim.AdamW(enc.parameters(), lr=1e-5, fused=True, capturable=args.cuda_graph)
-    host_srcs, host_pos = W.make_feature_pyramid(shapes, count, C, seed=99 + start, device="cpu", pin=True)
     srcs = [t.to(dev) for t in host_srcs]
-    pos = [t.to(dev) for t in host_pos]
-    pts_per_step = global_batch * S * M * L * P * layers
     loss_host = torch.zeros(1).pin_memory()
 
+    def decoder_body(x):
+        memory = x[0].detach().requires_grad_(not args.forward_only)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            outs, _ = enc(tgt, memory, refpoints_unsigmoid=refs, level_start_index=lsi_dev, spatial_shapes=ss_dev,
+                          valid_ratios=vr)
+            loss = sum(o.float().square().mean() for o in outs)
+        return loss
+
     def step_body(x):
+        if decoder_step:
+            if args.forward_only:
+                with torch.no_grad():
+                    return decoder_body(x)
+            buckets.zero()
+            loss = decoder_body(x)
+            loss.backward()
+            buckets.wait()
+            opt.step()
+            return loss.detach()
         if args.forward_only:
             with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=not args.fused_layers):
                 memory, _, _ = enc(x, None, pos)
@@ -495,12 +544,14 @@ def run_train_step(args):
         e2e_ms = D.max_over_ranks(e0.elapsed_time(e1), dev) / args.e2e_steps
         e2e = {"value": pts_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": args.e2e_steps,
                "h2d_bytes_per_step": sum(t.numel() * 4 for t in host_srcs), "d2h_bytes_per_step": 4,
-               "api": "MSDeformAttnTransformerEncoderOnly.forward/backward + GradientBuckets + AdamW; feature pyramid copied "
-                      "from pinned host memory every step, loss copied back"}
+               "api": ("TransformerDecoder.forward/backward + GradientBuckets + AdamW; encoder memory copied from pinned host "
+                       "memory every step, loss copied back") if decoder_step else
+                      ("MSDeformAttnTransformerEncoderOnly.forward/backward + GradientBuckets + AdamW; feature pyramid copied "
+                       "from pinned host memory every step, loss copied back")}
     if rank != 0:
         return 0
     peak, peak_src = measured_peak_gbs()
-    ab = W.algorithmic_bytes(count, S, S, M, C // M, L, P, 2)
+    ab = W.algorithmic_bytes(count, S, cfg["queries"] if decoder_step else S, M, C // M, L, P, 2)
     if args.fused_preop:        # sampling locations / attention weights never reach HBM: raw offsets + logits instead (same sizes)
         pass
     roofline = None
@@ -524,7 +575,8 @@ def run_train_step(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": args.workload, "global_batch": global_batch, "per_gpu_batch": count, "layers": layers,
-                   "levels": shapes, "queries": S, "heads": M, "head_dim": C // M, "points": P, "d_ffn": cfg["d_ffn"],
+                   "levels": shapes, "queries": cfg["queries"] if decoder_step else S, "heads": M, "head_dim": C // M,
+                   "points": P, "d_ffn": cfg["d_ffn"], "shared_value_proj": bool(args.shared_value_proj),
                    "fused_preop": bool(args.fused_preop or args.fused_layers), "fused_layers": bool(args.fused_layers),
                    "cuda_graph": bool(args.cuda_graph), "forward_only": bool(args.forward_only),
                    "optimizer": "AdamW(fused)", "autocast": "bf16",
@@ -564,7 +616,7 @@ def main():
         return subprocess.call(cmd)
     from vision_instance_seg_b200 import workloads as W
     try:
-        if W.CONFIGS[args.workload]["kind"] == "train_step":
+        if W.CONFIGS[args.workload]["kind"] in ("train_step", "decoder_step"):
             return run_train_step(args)
         return run_b200(args)
     finally:

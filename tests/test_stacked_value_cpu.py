@@ -113,6 +113,12 @@ def test_value_cache_is_per_forward_pass():
     src2.add_(1.0)                                             # in-place change of the memory: new projection
     proj.value_for(2, src2, None)
     assert len(calls) == 4
+    # the decoder layers each present a fresh `memory.transpose(0, 1)` view of the same memory: one projection
+    memory = torch.randn(6, 1, 64, dtype=torch.double, requires_grad=True)
+    n = len(calls)
+    for i in range(K):
+        proj.value_for(i, memory.transpose(0, 1), None)
+    assert len(calls) == n + 1
     unshare_value_proj(mods)
     assert all(m._stacked_value is None for m in mods)
 

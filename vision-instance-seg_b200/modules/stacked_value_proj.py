@@ -137,10 +137,18 @@ class StackedValueProj:
         self._clear()
 
     def _clear(self):
-        self._src = self._mask = self._views = self._value_all = self._shared = None
-        self._src_version = -1
-        self._grad_mode = None
+        self._src = self._mask = self._views = self._value_all = self._shared = self._key = None
         self._served = 0
+
+    @staticmethod
+    def _tensor_key(t: Optional[torch.Tensor]):
+        """Identity of a tensor's *contents and autograd origin*: the decoder layers call
+        ``cross_attn(..., memory.transpose(0, 1), ...)``, i.e. every layer presents a fresh view object of the same
+        memory, which must hit the cache; an in-place update (version bump) or another base tensor must not."""
+        if t is None:
+            return None
+        base = t._base if t._base is not None else t
+        return (id(base), t.data_ptr(), t._version, tuple(t.shape), t.stride(), t.dtype, t.requires_grad)
 
     def project(self, input_flatten: torch.Tensor, input_padding_mask: Optional[torch.Tensor]):
         """-> (views, value_all, shared): the K per-layer value views ``(N, S, M, D)``, the stacked tensor they alias and
@@ -159,14 +167,12 @@ class StackedValueProj:
     def value_for(self, index: int, input_flatten: torch.Tensor, input_padding_mask: Optional[torch.Tensor]):
         """Layer ``index``'s (view, value_all, shared); the stacked GEMM runs when a forward pass presents a memory tensor
         (or mask) that differs from the cached one, and the cache is dropped once all K layers have been served."""
-        hit = (self._views is not None and self._src is input_flatten and self._src_version == input_flatten._version
-               and self._mask is input_padding_mask and self._grad_mode == torch.is_grad_enabled())
-        if not hit:
+        key = (self._tensor_key(input_flatten), self._tensor_key(input_padding_mask), torch.is_grad_enabled())
+        if self._views is None or key != self._key:
             self._clear()
             self._views, self._value_all, self._shared = self.project(input_flatten, input_padding_mask)
-            self._src, self._mask = input_flatten, input_padding_mask
-            self._src_version = input_flatten._version
-            self._grad_mode = torch.is_grad_enabled()
+            self._src, self._mask = input_flatten, input_padding_mask        # keep them alive: the key holds addresses
+            self._key = key
         out = (self._views[index], self._value_all, self._shared)
         self._served += 1
         if self._served >= self.K:

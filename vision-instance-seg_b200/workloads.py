@@ -29,6 +29,10 @@ CONFIGS = {
     # 180 GB (~10 GB of saved activations per image).
     "cfg5_train_step_2048": dict(shapes=[(256, 256), (128, 128), (64, 64), (32, 32)], batch=8, dtype=torch.bfloat16,
                                  kind="train_step", layers=6, d_model=256, heads=8, points=4, d_ffn=2048),
+    # BASELINE.json configs[3] as a training step: the 9-layer deformable decoder (self-attention, cross-attention on the
+    # encoder memory, FFN) with 300 box queries, batch-sharded like the encoder step
+    "cfg4_decoder_step_300q": dict(shapes=[(128, 128), (64, 64), (32, 32), (16, 16)], batch=16, dtype=torch.bfloat16,
+                                   kind="decoder_step", layers=9, queries=300, d_model=256, heads=8, points=4, d_ffn=2048),
     # the same step at the cfg3 geometry (1024^2), for quick runs
     "cfg3_train_step_1024": dict(shapes=[(128, 128), (64, 64), (32, 32), (16, 16)], batch=16, dtype=torch.bfloat16,
                                  kind="train_step", layers=6, d_model=256, heads=8, points=4, d_ffn=2048),
