@@ -227,8 +227,11 @@ __device__ __forceinline__ void fused_prepare(float* myloc, float* myattn, const
 // =====================================================================================================
 // FUSED: `loc` / `attn` hold raw sampling offsets / attention logits and `ref` (N, Lq, L, R) the reference points
 // AT   : element type of `loc` / `attn` (float; the fused kernels also take the 16-bit value type)
+// Plain forward: 6 CTAs/SM (40 registers, 8 bytes of spill) instead of the 5 the compiler's 43 registers allow:
+// the kernel is bound by issue slots and L1TEX wavefronts, one more resident CTA hides more of the gather latency
+// (A/B on one box: 0.801 -> 0.780 ms at cfg3).  7 CTAs/SM spill ~100 bytes; the fused variant keeps its registers.
 template <typename T, int D, bool FUSED, typename AT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, FUSED ? 5 : 6)
 msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const AT* __restrict__ loc,
                     const AT* __restrict__ attn, const float* __restrict__ ref, int R, T* __restrict__ out,
