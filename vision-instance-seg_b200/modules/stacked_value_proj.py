@@ -73,7 +73,6 @@ class _SplitStackedValue(Function):
     @once_differentiable
     def backward(ctx, *grads):
         buf, written = ctx.shared.take()
-        K = ctx.shape[2]
         if buf is None or tuple(buf.shape) != tuple(ctx.shape):
             buf = torch.empty(ctx.shape, dtype=ctx.meta[0], device=ctx.meta[1])
             written = set()
