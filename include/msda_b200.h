@@ -68,8 +68,8 @@ enum {
   MSDA_BWD_DEFAULT = 0,
   /* 16-bit values: accumulate in an fp32 scratch with red.global.add.v4.f32 instead (2x the reduction bytes). */
   MSDA_BWD_GRAD_VALUE_FP32_ACCUM = 2,
-  /* Default mode, sparse levels.  A level with 2*Lq*P <= H_l*W_l (decoder cross-attention: a few hundred queries
-   * against 10^4 pixels; expected adds per element well below one) owns no accumulator rows: its contributions are
+  /* Default mode, sparse levels.  A level with 4*Lq*P <= H_l*W_l (decoder cross-attention: a few hundred queries
+   * against 10^4 pixels; at most one expected add per element) owns no accumulator rows: its contributions are
    * added, unscaled, with packed 16-bit reductions in the value dtype straight into the zeroed grad_value rows, so the
    * dense zero / sum / round passes over the accumulator (most of a decoder layer's backward) are paid for the coarse
    * levels only.  This flag switches that off (every level goes through the fp16 buckets). */

@@ -42,7 +42,7 @@ for seed in range(lo, hi):
     ss = torch.as_tensor(shapes, dtype=torch.long)
     S = int(ss.prod(1).sum())
     N, Lq, M, D, P, K = c["N"], c["Lq"], c["M"], c["D"], c["P"], c["K"]
-    sparse = [2 * Lq * P <= h * w for h, w in shapes]
+    sparse = [4 * Lq * P <= h * w for h, w in shapes]
     c["sparse"] = sparse
     dtype = rng.choice([torch.float32, torch.bfloat16, torch.float16])
     layer = rng.randrange(K)

@@ -20,9 +20,9 @@ NO_SPARSE = 4        # MSDA_BWD_NO_SPARSE_DIRECT
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("shapes,Lq", [
-    ([(32, 32), (16, 16), (8, 8), (4, 4)], 40),      # levels 0, 1 sparse (2*40*4 <= 1024, 256), levels 2, 3 bucketed
-    ([(32, 32), (16, 16)], 30),                      # every level sparse: the rounding pass has nothing to do
-    ([(6, 4), (3, 2)], 3),                           # tiny, non-square, boundary of the criterion (2*3*4 == 24)
+    ([(32, 32), (16, 16), (8, 8), (4, 4)], 16),      # levels 0, 1 sparse (4*16*4 <= 1024, 256), levels 2, 3 bucketed
+    ([(32, 32), (16, 16)], 15),                      # every level sparse: the rounding pass has nothing to do
+    ([(4, 4), (3, 2)], 1),                           # tiny, non-square, boundary of the criterion (4*1*4 == 16)
     ([(20, 12), (5, 3), (40, 24)], 25),              # sparse levels not in order of size
 ])
 def test_sparse_levels_add_directly_into_grad_value(ops, dtype, shapes, Lq):
@@ -68,7 +68,7 @@ def test_sparse_levels_untouched_rows_are_exact_zeros(ops):
 
 
 def test_config4_decoder_shape_uses_direct_levels_and_matches_bucketed(ops):
-    """cfg4 geometry (300 queries against 128^2 .. 16^2): levels 0 and 1 are sparse.  Both accumulation modes must
+    """cfg4 geometry (300 queries against 128^2 .. 16^2): level 0 is sparse (4*300*4 <= 16 384).  Both accumulation modes must
     agree with the oracle; 2 images keep the oracle quick."""
     from vision_instance_seg_b200 import workloads as W
     cfg = W.CONFIGS["cfg4_decoder_300q_bf16"]

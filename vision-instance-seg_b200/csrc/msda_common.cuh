@@ -8,6 +8,16 @@
 namespace msda {
 
 constexpr int kMaxLevels = 32;
+#ifndef MSDA_SPARSE_FACTOR
+#define MSDA_SPARSE_FACTOR 4
+#endif
+// a level is "sparse" (its grad_value contributions are added directly, see build_accum_layout) when
+// kSparseFactor * Lq * P <= H_l * W_l, i.e. it expects at most 4 / kSparseFactor corner rows per pixel row.
+// 4 (one expected add per row) rather than 2: with 2 the 64x64 level of the cfg4 decoder shape also qualified, and
+// when all 300 queries crowd into 3 % of the image the packed bf16 adds into that level lost up to 15 % of
+// grad_value (tests/dev/gpu_sparse_accuracy.py); with 4 the direct mode stays within a few 1e-3 of the fp16 buckets
+// over the whole clustering range measured
+constexpr long long kSparseFactor = MSDA_SPARSE_FACTOR;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 
@@ -122,7 +132,7 @@ __device__ __forceinline__ void load_level_meta(LevelMeta& meta, const int64_t* 
 // accum_rows_bound() to size the buffer.
 //
 // Sparse levels (decoder cross-attention: a few hundred queries against 10^4 pixels).  When a level expects at most
-// one corner row per two pixel rows (four corner rows per point: 4*Lq*P <= 2*H_l*W_l) almost every element receives
+// one corner row per pixel row (four corner rows per point: 4*Lq*P <= H_l*W_l) almost every element receives
 // zero or one add, and a packed 16-bit add straight into grad_value is then as accurate as accumulating anywhere
 // else and rounding once.  Such a level gets K_l = 0: its contributions are added, unscaled, into the (zeroed)
 // grad_value rows in the value dtype, it owns no accumulator rows, and the rounding pass skips it -- the dense zero /
@@ -142,7 +152,7 @@ __device__ __forceinline__ void build_accum_layout(LevelMeta& meta, int L, int L
       const long long hw = static_cast<long long>(meta.H[l]) * meta.W[l];
       const long long adds = hw > 0 ? (static_cast<long long>(Lq) * P + hw - 1) / hw : 1;
       const int K = static_cast<int>((adds + depth - 1) / depth);
-      const bool direct = sparse_direct && hw > 0 && 2ll * Lq * P <= hw;
+      const bool direct = sparse_direct && hw > 0 && kSparseFactor * Lq * P <= hw;
       meta.accK[l] = direct ? 0 : (K < 1 ? 1 : K);
       meta.accBase[l] = base;
       meta.dirOff[l] = dir;

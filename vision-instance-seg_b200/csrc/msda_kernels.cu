@@ -379,7 +379,7 @@ __device__ __forceinline__ float f16_accum_scale(const uint32_t* __restrict__ ct
 // FUSED   : `loc` / `attn` hold raw sampling offsets / attention logits, `ref` (N, Lq, L, R) the reference points;
 //           `grad_loc` / `grad_attn` receive the gradients of the raw offsets / logits (see fused_prepare).
 // AT      : element type of `loc` / `attn` / `grad_loc` / `grad_attn` (float; fused kernels also the 16-bit value type)
-// SPARSE  : GV16 only; some level may be sparse (2*Lq*P <= H_l*W_l <= S, decided on the host from Lq, P, S) and then
+// SPARSE  : GV16 only; some level may be sparse (4*Lq*P <= H_l*W_l <= S, decided on the host from Lq, P, S) and then
 //           adds straight into grad_value (build_accum_layout).  A separate instantiation because the extra
 //           level-uniform branch and addressing in the reduction loop cost the dense encoder shapes ~8 %.
 template <typename T, int D, bool GV16, bool FUSED, typename AT, bool SPARSE>
@@ -1067,8 +1067,8 @@ MSDA_LAUNCHER int launch_bwd(const Problem& pr, const void* value, const int64_t
   constexpr bool k16 = sizeof(T) == 2;
   const bool use16 = k16 && !(flags & MSDA_BWD_GRAD_VALUE_FP32_ACCUM) && vec_supported<T>(pr);
   const int depth = accum_depth(flags);
-  // a level can only be sparse (2*Lq*P <= H_l*W_l) if 2*Lq*P <= S: decided here, the levels themselves on the device
-  const bool sparse_direct = use16 && !(flags & MSDA_BWD_NO_SPARSE_DIRECT) && 2ll * pr.Lq * pr.P <= pr.S;
+  // a level can only be sparse (4*Lq*P <= H_l*W_l) if 4*Lq*P <= S: decided here, the levels themselves on the device
+  const bool sparse_direct = use16 && !(flags & MSDA_BWD_NO_SPARSE_DIRECT) && kSparseFactor * pr.Lq * pr.P <= pr.S;
   // strided grad_value: the vector kernels with direct (fp32 / fp64-free) or fp16-bucket accumulation only
   if (pr.strided() && (!vec_supported<T>(pr) || std::is_same<T, double>::value || (k16 && !use16))) return MSDA_ERR_BAD_STRIDE;
   const int gstride = pr.grad_stride();
