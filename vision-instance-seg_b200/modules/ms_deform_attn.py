@@ -125,6 +125,12 @@ class MSDeformAttn(nn.Module):
             stacked = proj.value_for(index, input_flatten, input_padding_mask)   # (view, value_all, grad state)
             value = stacked[0]
         else:
+            if input_flatten.is_cuda and not input_flatten.is_contiguous():
+                # the decoder passes `memory.transpose(0, 1)`; on a strided operand F.linear runs matmul plus a separate
+                # broadcast add of the bias over the whole output.  One fused transpose (+ autocast cast) to a dense
+                # operand keeps the bias in the GEMM epilogue -- same stock Linear, same numbers as on a dense input.
+                dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else input_flatten.dtype
+                input_flatten = input_flatten.to(dtype=dtype, memory_format=torch.contiguous_format)
             value = self.value_proj(input_flatten)
             if input_padding_mask is not None:
                 value = value.masked_fill(input_padding_mask[..., None], float(0))
