@@ -140,6 +140,16 @@ int msda_backward_strided(const void* value, long long value_pixel_stride,
                           int N, int S, int M, int D, int Lq, int L, int P,
                           int value_dtype, int im2col_step, int flags, void* stream);
 
+/*
+ * Tiled kernels for the dense call site (csrc/msda_tiled.cuh).  When every value pixel is also a query (Lq == S: the
+ * pixel-decoder encoder layers), values are 16-bit and the head dim is 32, msda_forward / msda_backward keep per-tile
+ * windows of `value` in shared memory and sum grad_value per destination row before it leaves the SM.  Results do not
+ * depend on the mode (points that leave their window take the direct path); mode 0 forces the direct kernels for every
+ * call of the process, mode 1 (default; environment MSDA_B200_TILED=0|1 on first use) enables the tiled ones.  Returns
+ * the previous mode.
+ */
+int msda_set_tiled_mode(int mode);
+
 /* Number of kernel launches (not memsets) the last forward/backward call on this thread enqueued;
  * used by bench.py to report `gpu_launches`. */
 int msda_last_launch_count(void);
@@ -156,7 +166,9 @@ long long msda_total_launch_count(void);
  * max_records (duration in ms, kind) pairs in call order, frees them and returns how many it wrote.
  * These two calls are the only ones in the library that create events or block the host.
  */
-enum { MSDA_KERNEL_FORWARD = 1, MSDA_KERNEL_BACKWARD = 2 };
+enum { MSDA_KERNEL_FORWARD = 1, MSDA_KERNEL_BACKWARD = 2,
+       /* tiled backward (dense call site): the two kernels that replace MSDA_KERNEL_BACKWARD */
+       MSDA_KERNEL_BACKWARD_DOTS = 3, MSDA_KERNEL_BACKWARD_SCATTER = 4 };
 int msda_profile_enable(int on);
 int msda_profile_collect(float* ms, int* kinds, int max_records);
 

@@ -26,7 +26,7 @@ def test_header_declares_and_library_exports_every_symbol(built_library):
     lib = ctypes.CDLL(built_library)
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/*.h but not exported"
-    assert pkg.load_library().msda_abi_version() == 4
+    assert pkg.load_library().msda_abi_version() == 5
 
 
 def test_error_strings(built_library):

@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = (
     "msda_backward",
     "msda_forward_strided",
     "msda_backward_strided",
+    "msda_set_tiled_mode",
     "msda_last_launch_count",
     "msda_total_launch_count",
     "msda_profile_enable",
@@ -62,6 +63,8 @@ def _declare(lib):
     lib.msda_abi_version.argtypes = []
     lib.msda_error_string.restype = ctypes.c_char_p
     lib.msda_error_string.argtypes = [i]
+    lib.msda_set_tiled_mode.restype = i
+    lib.msda_set_tiled_mode.argtypes = [i]
     lib.msda_last_launch_count.restype = i
     lib.msda_last_launch_count.argtypes = []
     lib.msda_forward.restype = i

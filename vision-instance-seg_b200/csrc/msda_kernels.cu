@@ -708,6 +708,9 @@ msda_round_f16_buckets_kernel(const __half* __restrict__ acc, T* __restrict__ ds
   }
 }
 
+// Tiled kernels for the dense encoder call site (Lq == S): shared-memory value windows, sorted grad_value sums
+#include "msda_tiled.cuh"
+
 // =====================================================================================================
 // Compatibility path: any D, any dtype (incl. float64).  One warp per (b, q, m) pair.
 // =====================================================================================================
@@ -858,10 +861,22 @@ static size_t f16_scratch_bytes(int N, int S, int M, int D, int Lq, int L, int P
 #if defined(MSDA_SPLIT_BUILD) && !defined(MSDA_TU_ABI)
 extern thread_local int g_last_launches;
 extern std::atomic<long long> g_total_launches;
+extern std::atomic<int> g_tiled_mode;
 #else
 thread_local int g_last_launches = 0;
 std::atomic<long long> g_total_launches{0};
+std::atomic<int> g_tiled_mode{-1};         // msda_set_tiled_mode(); -1 = take MSDA_B200_TILED from the environment on first use
 #endif
+
+static bool tiled_enabled() {
+  int m = g_tiled_mode.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = std::getenv("MSDA_B200_TILED");
+    m = (e && e[0] == '0') ? 0 : 1;
+    g_tiled_mode.store(m, std::memory_order_relaxed);
+  }
+  return m != 0;
+}
 
 // ---- optional per-launch timing of the dominant kernels (bench.py's roofline leg) --------------------
 struct ProfileRecord { cudaEvent_t start, stop; int kind; };
@@ -982,9 +997,99 @@ static int launch_fwd_vec(const Problem& pr, const void* value, const int64_t* s
   return launch_fwd_vec_impl<T, D, false, float>(pr, value, shapes, lsi, loc, attn, out, st);
 }
 
+// ---- tiled kernels (msda_tiled.cuh): dense call site, 16-bit values, head dim 32 ---------------------------
+// What the host can check without reading the shape tensor; everything else (level nesting, halo, window capacity) is
+// decided on the device, where a point that does not fit its window takes the slow path.
+template <typename T> static bool tiled_supported(const Problem& pr) {
+  return sizeof(T) == 2 && pr.D == tiled::kD && pr.Lq == pr.S && pr.ref == nullptr && pr.L <= tiled::kMaxL &&
+         pr.L * pr.P <= tiled::kMaxLP && vec_supported<T>(pr) && tiled_enabled();
+}
+
+// persistent grid: one resident wave of the kernel (the two device queries are cached per kernel and thread)
+template <typename K>
+static int tiled_grid(K kernel, int threads, size_t dyn_smem) {
+  struct Entry { const void* fn; int per_sm; };
+  static thread_local Entry cache[16];
+  static thread_local int cached = 0, sms = 0;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  for (int i = 0; i < cached; ++i)
+    if (cache[i].fn == key) return cache[i].per_sm * sms;
+  int dev = 0;
+  if (sms == 0 && (cudaGetDevice(&dev) != cudaSuccess ||
+                   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1))
+    sms = 148;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  if (cached < 16) cache[cached++] = Entry{key, per_sm};
+  return per_sm * sms;
+}
+
+static size_t tiled_fwd_smem(int L, int P) {
+  const int LP8 = (L * P + 7) & ~7;
+  return static_cast<size_t>(tiled::kWinRowsCap + 2) * tiled::kRowBytes + static_cast<size_t>(tiled::kQC) * LP8 * 3 * sizeof(uint32_t);
+}
+static size_t tiled_dots_smem(int L, int P) {
+  const int LP8 = (L * P + 7) & ~7;
+  return static_cast<size_t>(tiled::kWinRowsCap + 2) * tiled::kRowBytes + static_cast<size_t>(tiled::kQC) * LP8 * (sizeof(uint32_t) + sizeof(float4));
+}
+
+template <typename T>
+static int launch_fwd_tiled(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
+                            const void* loc, const void* attn, void* out, cudaStream_t st) {
+  auto kernel = tiled::msda_fwd_tiled_kernel<T>;
+  const size_t smem = tiled_fwd_smem(pr.L, pr.P);
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const int grid = tiled_grid(kernel, tiled::kThreadsT, smem);
+  ScopedKernelTimer timer(MSDA_KERNEL_FORWARD, st);
+  kernel<<<grid, tiled::kThreadsT, smem, st>>>(static_cast<const T*>(value), shapes, lsi, static_cast<const float*>(loc),
+                                               static_cast<const float*>(attn), static_cast<T*>(out), pr.N, pr.S, pr.M,
+                                               pr.Lq, pr.L, pr.P, pr.value_stride());
+  ++g_last_launches, ++g_total_launches;
+  return static_cast<int>(cudaGetLastError());
+}
+
+// grad_sampling_loc / grad_attn_weight (+ max|grad_out| into ctrl[0]), then grad_value into the fp16 accumulator
+template <typename T>
+static int launch_bwd_tiled(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
+                            const void* loc, const void* attn, const void* go, __half* acc16, uint32_t* ctrl,
+                            void* gloc, void* gattn, int depth, cudaStream_t st) {
+  {
+    auto kernel = tiled::msda_bwd_dots_tiled_kernel<T>;
+    const size_t smem = tiled_dots_smem(pr.L, pr.P);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const int grid = tiled_grid(kernel, tiled::kThreadsT, smem);
+    ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD_DOTS, st);
+    kernel<<<grid, tiled::kThreadsT, smem, st>>>(static_cast<const T*>(value), shapes, lsi, static_cast<const float*>(loc),
+                                                 static_cast<const float*>(attn), static_cast<const T*>(go),
+                                                 static_cast<float*>(gloc), static_cast<float*>(gattn), ctrl, pr.N, pr.S,
+                                                 pr.M, pr.Lq, pr.L, pr.P, pr.value_stride());
+    ++g_last_launches, ++g_total_launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  {
+    auto kernel = tiled::msda_bwd_scatter_tiled_kernel<T>;
+    const size_t smem = tiled::kScSmemBytes;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const int grid = tiled_grid(kernel, tiled::kScThreads, smem);
+    ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD_SCATTER, st);
+    kernel<<<grid, tiled::kScThreads, smem, st>>>(shapes, lsi, static_cast<const float*>(loc), static_cast<const float*>(attn),
+                                                  static_cast<const T*>(go), acc16, ctrl, pr.N, pr.S, pr.M, pr.Lq, pr.L,
+                                                  pr.P, depth);
+    ++g_last_launches, ++g_total_launches;
+    return static_cast<int>(cudaGetLastError());
+  }
+}
+
 template <typename T>
 MSDA_LAUNCHER int launch_fwd(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
                       const void* loc, const void* attn, void* out, cudaStream_t st) {
+  if constexpr (sizeof(T) == 2) {
+    if (tiled_supported<T>(pr)) return launch_fwd_tiled<T>(pr, value, shapes, lsi, loc, attn, out, st);
+  }
   if constexpr (!std::is_same<T, double>::value) {
     if (vec_supported<T>(pr)) {
       switch (pr.D) {
@@ -1066,7 +1171,11 @@ MSDA_LAUNCHER int launch_bwd(const Problem& pr, const void* value, const int64_t
   const size_t n_value = static_cast<size_t>(pr.N) * pr.S * pr.M * pr.D;
   constexpr bool k16 = sizeof(T) == 2;
   const bool use16 = k16 && !(flags & MSDA_BWD_GRAD_VALUE_FP32_ACCUM) && vec_supported<T>(pr);
-  const int depth = accum_depth(flags);
+  // tiled kernels: one reduction per (destination row, tile) reaches the accumulator -- at most a few hundred adds per
+  // element on the coarsest level of a pyramid -- so a single copy per level (no buckets) keeps the fp16 error at ~2e-3
+  bool tiled = false;
+  if constexpr (k16) tiled = use16 && tiled_supported<T>(pr);
+  const int depth = tiled ? 0xffff : accum_depth(flags);
   // a level can only be sparse (4*Lq*P <= H_l*W_l) if 4*Lq*P <= S: decided here, the levels themselves on the device
   const bool sparse_direct = use16 && !(flags & MSDA_BWD_NO_SPARSE_DIRECT) && kSparseFactor * pr.Lq * pr.P <= pr.S;
   // strided grad_value: the vector kernels with direct (fp32 / fp64-free) or fp16-bucket accumulation only
@@ -1096,7 +1205,7 @@ MSDA_LAUNCHER int launch_bwd(const Problem& pr, const void* value, const int64_t
   }
   if (e != cudaSuccess) return static_cast<int>(e);
   if constexpr (k16) {
-    if (use16) {
+    if (use16 && !tiled) {
       const size_t n8 = static_cast<size_t>(pr.N) * pr.Lq * pr.M * pr.D / 8;     // D is a multiple of 16 here
       const int grid = static_cast<int>(std::min<size_t>((n8 + 255) / 256, 148 * 8));
       msda_absmax_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(go), n8, ctrl);
@@ -1107,8 +1216,14 @@ MSDA_LAUNCHER int launch_bwd(const Problem& pr, const void* value, const int64_t
   }
   int rc;
   bool done = false;
+  if constexpr (k16) {
+    if (tiled) {
+      rc = launch_bwd_tiled<T>(pr, value, shapes, lsi, loc, attn, go, acc16, ctrl, gloc, gattn, depth, st);
+      done = true;
+    }
+  }
   if constexpr (!std::is_same<T, double>::value) {
-    if (vec_supported<T>(pr)) {
+    if (!done && vec_supported<T>(pr)) {
       float* gv32 = k16 ? static_cast<float*>(scratch) : static_cast<float*>(gv);
       void* gvd = sparse_direct ? gv : nullptr;                      // sparse levels add straight into grad_value
       const int gvs = (k16 && !use16) ? pr.M * pr.D : gstride;       // the fp32 scratch of 16-bit values is dense
@@ -1195,7 +1310,7 @@ MSDA_LAUNCHERS_OF(, __half)
 // =====================================================================================================
 using namespace msda;
 
-extern "C" int msda_abi_version(void) { return 4; }
+extern "C" int msda_abi_version(void) { return 5; }
 
 extern "C" const char* msda_error_string(int code) {
   switch (code) {
@@ -1215,6 +1330,12 @@ extern "C" const char* msda_error_string(int code) {
   }
   if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
   return "unknown msda error";
+}
+
+extern "C" int msda_set_tiled_mode(int mode) {
+  const int prev = tiled_enabled() ? 1 : 0;
+  g_tiled_mode.store(mode != 0 ? 1 : 0);
+  return prev;
 }
 
 extern "C" int msda_last_launch_count(void) { return g_last_launches; }
