@@ -125,10 +125,10 @@ if __name__ == "__main__":
         ("wide", [(6, 200), (3, 100)], 1, bf, "encoder", {}),
         ("tall", [(300, 5), (150, 3)], 1, bf, "encoder", {}),
     ]
-    for name, shapes, batch, dtype, kind, kw in cases:
-        r = case(name, shapes, batch, dtype, kind, oracle=oracle, **kw)
-        ok = ok and r.get("ok", True)
     if "--time" in sys.argv:
         timing([(128, 128), (64, 64), (32, 32), (16, 16)], 16, bf)
         timing([(128, 128), (64, 64), (32, 32), (16, 16)], 16, bf, kind="uniform")
+    for name, shapes, batch, dtype, kind, kw in cases:
+        r = case(name, shapes, batch, dtype, kind, oracle=oracle, **kw)
+        ok = ok and r.get("ok", True)
     print("ALL_OK" if ok else "SOME_FAILED", flush=True)

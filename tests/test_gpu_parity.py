@@ -84,7 +84,7 @@ def test_upstream_check_forward_equal_with_pytorch(ops):
         assert rel_to_max(out, t["out"]) < TOL[dtype]
 
 
-@pytest.mark.parametrize("channels", [30, 32, 64, 71, 1025])
+@pytest.mark.parametrize("channels", [30, 32, 64, 71, 1025, 2048, 3096])
 def test_upstream_check_gradient_numerical(ops, channels):
     """Restated upstream check_gradient_numerical: torch.autograd.gradcheck of the fp64 CUDA path."""
     value, ss, lsi, loc, attn, _ = random_problem(1, 2, channels, 2, [(6, 4), (3, 2)], 2, seed=3, loc_range=(0.05, 0.95))
@@ -408,3 +408,71 @@ def test_host_pipeline_matches_device_resident_path(ops):
         assert torch.equal(out.cpu(), h_out[0])
         assert rel_to_max(h_out[1], gv) < 1e-2          # fp32 atomics: order-dependent in the last bits, then bf16 rounding
         assert torch.equal(gl.cpu(), h_out[2]) and torch.equal(ga.cpu(), h_out[3])
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: non-finite values, full-size per-image comparison
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float64])
+@pytest.mark.parametrize("bad", [float("nan"), float("inf")])
+def test_points_that_fail_the_gate_never_touch_value(ops, dtype, bad):
+    """Upstream skips a sampling point unless -1 < h_im < H and -1 < w_im < W; it never loads a pixel for it.  Plant
+    NaN / Inf at the four corner pixels of every level -- the pixels a clamped address of an outside point would hit --
+    keep every valid footprint away from them, and send half of the points far outside: all four results must stay
+    finite and equal to the oracle's (which runs on the same planted values)."""
+    D = 32 if dtype != torch.float64 else 6
+    value, ss, lsi, loc, attn, go = random_problem(2, 4, D, 40, [(12, 10), (6, 7), (5, 5)], 4, seed=21, loc_range=(0.3, 0.7))
+    g = torch.Generator().manual_seed(2)
+    outside = torch.rand(loc.shape[:-1], generator=g) < 0.5
+    far = torch.where(torch.rand(loc.shape, generator=g) < 0.5, torch.full_like(loc, -0.75), torch.full_like(loc, 1.75))
+    loc = torch.where(outside[..., None], far, loc)
+    value = value.clone()
+    for (H, W), start in zip(ss.tolist(), lsi.tolist()):
+        for y, x in ((0, 0), (0, W - 1), (H - 1, 0), (H - 1, W - 1)):
+            value[:, start + y * W + x] = bad
+    got = run_cuda(ops, value, ss, lsi, loc, attn, go, dtype)
+    want = oracle_on_rounded_inputs(value, ss, loc, attn, go, dtype)
+    for name, a, b in zip(("out", "grad_value", "grad_loc", "grad_attn"), got, want):
+        assert torch.isfinite(b).all(), f"oracle {name} not finite: the test inputs are wrong"
+        assert torch.isfinite(a).all(), f"{name}: non-finite values leaked from pixels no valid point samples"
+        assert rel_to_max(a, b) < TOL[dtype], name
+
+
+def _compare_per_image(ops, v, ss, lsi, loc, attn, go, smooth_eps=1e-3):
+    """CUDA on the whole batch, oracle image by image (fp32 on the CPU, seconds per image)."""
+    got = run_cuda(ops, v.float(), ss, lsi, loc, attn, go, torch.bfloat16)
+    wh = torch.stack([ss[:, 1], ss[:, 0]], -1).to(torch.float32)[None, None, None, :, None, :]
+    worst = {}
+    for b in range(v.shape[0]):
+        want = ms_deform_attn_oracle_grads(v[b:b + 1].float(), ss, loc[b:b + 1], attn[b:b + 1],
+                                           go[b:b + 1].to(torch.bfloat16).float(), dtype=torch.float32)
+        px = loc[b:b + 1] * wh - 0.5
+        smooth = ((px - px.round()).abs() > smooth_eps).all(-1, keepdim=True).expand_as(loc[b:b + 1])
+        for name, a, w in zip(("out", "grad_value", "grad_loc", "grad_attn"), got, want):
+            a, w = a[b:b + 1].detach().float().cpu(), w.float()
+            if name == "grad_loc":          # away from integer pixel lines, where the bilinear derivative jumps
+                a, w = a * smooth, w * smooth
+            worst[name] = max(worst.get(name, 0.0), rel_to_max(a, w))
+    return worst
+
+
+def test_config3_full_batch_against_the_oracle_per_image(ops):
+    """BASELINE.json configs[2] at its full size (N = 16, 21 760 queries, bf16): every image against the oracle."""
+    from vision_instance_seg_b200 import workloads as W
+    cfg = W.CONFIGS["cfg3_swinl_1024_bf16"]
+    v, ss, lsi, loc, attn = W.make_encoder_inputs(cfg["shapes"], cfg["batch"], torch.bfloat16, device="cpu", seed=99)
+    go = torch.randn(cfg["batch"], loc.shape[1], 256, generator=torch.Generator().manual_seed(9))
+    worst = _compare_per_image(ops, v, ss, lsi, loc, attn, go)
+    for name, err in worst.items():
+        assert err < 2e-2, f"{name}: {err:.3e}"
+
+
+def test_config4_full_batch_against_the_oracle_per_image(ops):
+    """BASELINE.json configs[3] at its full size (N = 16, 300 box queries, bf16), default backward mode."""
+    from vision_instance_seg_b200 import workloads as W
+    cfg = W.CONFIGS["cfg4_decoder_300q_bf16"]
+    v, ss, lsi, loc, attn = W.make_decoder_inputs(cfg["shapes"], cfg["batch"], torch.bfloat16, queries=300, device="cpu", seed=5)
+    go = torch.randn(cfg["batch"], 300, 256, generator=torch.Generator().manual_seed(10))
+    worst = _compare_per_image(ops, v, ss, lsi, loc, attn, go)
+    for name, err in worst.items():
+        assert err < 2e-2, f"{name}: {err:.3e}"

@@ -24,6 +24,12 @@ from .modules import (MSDeformAttn, set_fused_encoder_layers, set_fused_preop, s
 
 
 
+def set_tiled_mode(enabled: bool) -> bool:
+    """Switch the opt-in tiled kernels of the dense call site (Lq == S, 16-bit values, head dim 32; see
+    include/msda_b200.h ``msda_set_tiled_mode``) on or off for this process; returns the previous setting."""
+    return bool(load_library().msda_set_tiled_mode(1 if enabled else 0))
+
+
 def install_as_upstream_extension(name: str = "MultiScaleDeformableAttention"):
     """Register this package's stand-in under the import name of upstream's compiled extension, so that an unmodified
     MaskDINO / Mask2Former / Deformable-DETR checkout — whose ``ops/functions/ms_deform_attn_func.py`` does
@@ -42,4 +48,4 @@ def install_as_upstream_extension(name: str = "MultiScaleDeformableAttention"):
 
 
 __all__ = ["MSDeformAttn", "MSDeformAttnFunction", "MSDeformAttnFusedFunction", "MultiScaleDeformableAttention",
-           "set_fused_preop", "set_fused_encoder_layers", "share_value_proj", "unshare_value_proj", "install_as_upstream_extension", "load_library", "library_path"]
+           "set_fused_preop", "set_fused_encoder_layers", "share_value_proj", "unshare_value_proj", "install_as_upstream_extension", "load_library", "library_path", "set_tiled_mode"]

@@ -209,9 +209,15 @@ __device__ __forceinline__ Footprint<F> make_footprint(F x, F y, int H, int W) {
 // Zero padding is folded into the weights: every corner address is clamped into the level (so all four
 // loads are unconditional) and an out-of-range corner gets weight 0.  The clamped address of an invalid
 // corner is always another, valid corner of the same footprint, so non-finite values propagate exactly as
-// upstream.  (A point that fails the gate altogether reads pixel (0,0)-clamped data with weight 0.)
+// upstream.  A point that fails the gate altogether must not touch `value` (upstream skips it, and 0 * NaN would
+// leak a non-finite pixel into the result): the kernels point such a point at kZeroBlock with a zero pixel stride
+// (gated_base / gated_stride below), so its four loads stay unconditional and read zeros.
 // ---------------------------------------------------------------------------------------------------
+// 16 zero bytes: what a sampling point that fails upstream's gate reads instead of `value` (see make_taps)
+static __device__ uint4 kZeroBlock = {0u, 0u, 0u, 0u};
+
 struct Taps {
+  bool inside;                     // upstream's point-level gate
   int i00, i01, i10, i11;          // pixel indices inside the level, always in range
   float hhm, lhm, hwm, lwm;        // hh/lh/hw/lw with the row / column validity (and the gate) folded in
   float Tm, Bm, Lm, Rm;            // 1.0f / 0.0f validity of top / bottom row and left / right column
@@ -228,6 +234,7 @@ __device__ __forceinline__ Taps make_taps(float x, float y, int H, int W, float 
   const float h_im = __fsub_rn(__fmul_rn(y, Hf), 0.5f);
   const float w_im = __fsub_rn(__fmul_rn(x, Wf), 0.5f);
   const bool inside = (h_im > -1.f) && (w_im > -1.f) && (h_im < Hf) && (w_im < Wf);
+  t.inside = inside;
   float lh, lw; int iy, ix;
   floor_split(h_im, lh, iy);
   floor_split(w_im, lw, ix);
@@ -241,6 +248,11 @@ __device__ __forceinline__ Taps make_taps(float x, float y, int H, int W, float 
   t.i00 = yt * W + xl; t.i01 = yt * W + xr; t.i10 = yb * W + xl; t.i11 = yb * W + xr;
   return t;
 }
+
+__device__ __forceinline__ const char* gated_base(const Taps& t, const char* level_base) {
+  return t.inside ? level_base : reinterpret_cast<const char*>(&kZeroBlock);
+}
+__device__ __forceinline__ uint32_t gated_stride(const Taps& t, uint32_t pix_bytes) { return t.inside ? pix_bytes : 0u; }
 
 // ---- acc[i] += w * v[i] over the VEC elements of one 16-byte vector -----------------------------------
 // fp32 values: plain FFMA with the fp32 weight.  16-bit values: Blackwell's mixed-precision FMA

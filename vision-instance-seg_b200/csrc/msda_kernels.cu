@@ -290,11 +290,14 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   // one sampling point: four unconditional 16-byte corner loads + the weighted accumulation
   auto sample = [&](float x, float y, float a, int H, int W, float Hf, float Wf, const char* vl) {
     const Taps t = make_taps(x, y, H, W, Hf, Wf);
-    // pixel index * pixel stride fits 32 bits (validated on the host): one IMAD.WIDE per corner
-    const uint4 u00 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i00) * pix_bytes));
-    const uint4 u01 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i01) * pix_bytes));
-    const uint4 u10 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i10) * pix_bytes));
-    const uint4 u11 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i11) * pix_bytes));
+    // pixel index * pixel stride fits 32 bits (validated on the host): one IMAD.WIDE per corner; a point that fails
+    // the gate reads the zero block instead of `value`
+    const char* vg = gated_base(t, vl);
+    const uint32_t pg = gated_stride(t, pix_bytes);
+    const uint4 u00 = ldg16(vg + static_cast<size_t>(static_cast<uint32_t>(t.i00) * pg));
+    const uint4 u01 = ldg16(vg + static_cast<size_t>(static_cast<uint32_t>(t.i01) * pg));
+    const uint4 u10 = ldg16(vg + static_cast<size_t>(static_cast<uint32_t>(t.i10) * pg));
+    const uint4 u11 = ldg16(vg + static_cast<size_t>(static_cast<uint32_t>(t.i11) * pg));
     const float ah = t.hhm * a, al = t.lhm * a;
     axpy16<T>(acc, u00, make_weight<T>(ah * t.hwm));
     axpy16<T>(acc, u01, make_weight<T>(ah * t.lwm));
@@ -320,11 +323,12 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       const float2 xy = *reinterpret_cast<const float2*>(myloc + 2 * (l * P + p));
       const float a = myattn[l * P + p];
       const Taps t = make_taps(xy.x, xy.y, H, W, Hf, Wf);
-      // pixel index * pixel stride fits 32 bits (validated on the host): one IMAD.WIDE per corner
-      const uint4 u00 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i00) * pix_bytes));
-      const uint4 u01 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i01) * pix_bytes));
-      const uint4 u10 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i10) * pix_bytes));
-      const uint4 u11 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i11) * pix_bytes));
+      const char* vg = gated_base(t, vl);
+      const uint32_t pg = gated_stride(t, pix_bytes);
+      const uint4 u00 = ldg16(vg + static_cast<size_t>(static_cast<uint32_t>(t.i00) * pg));
+      const uint4 u01 = ldg16(vg + static_cast<size_t>(static_cast<uint32_t>(t.i01) * pg));
+      const uint4 u10 = ldg16(vg + static_cast<size_t>(static_cast<uint32_t>(t.i10) * pg));
+      const uint4 u11 = ldg16(vg + static_cast<size_t>(static_cast<uint32_t>(t.i11) * pg));
       const float ah = t.hhm * a, al = t.lhm * a;
       axpy16<T>(acc, u00, make_weight<T>(ah * t.hwm));
       axpy16<T>(acc, u01, make_weight<T>(ah * t.lwm));
@@ -503,11 +507,12 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
         const float2 xy = *reinterpret_cast<const float2*>(myloc + 2 * lp);
         const float a = myattn[lp];
         const Taps t = make_taps(xy.x, xy.y, H, W, Hf, Wf);
-        const char* vl = vb + lvl_pix * pix_bytes;
-        const uint4 u00 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i00) * pix_bytes));
-        const uint4 u01 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i01) * pix_bytes));
-        const uint4 u10 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i10) * pix_bytes));
-        const uint4 u11 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i11) * pix_bytes));
+        const char* vl = gated_base(t, vb + lvl_pix * pix_bytes);      // zero block for a point that fails the gate
+        const uint32_t pg = gated_stride(t, pix_bytes);
+        const uint4 u00 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i00) * pg));
+        const uint4 u01 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i01) * pg));
+        const uint4 u10 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i10) * pg));
+        const uint4 u11 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i11) * pg));
 
         // ---- grad_value: (corner weight * attn) * grad_out, scattered with packed reductions ----
         if (active) {
@@ -865,14 +870,14 @@ extern std::atomic<int> g_tiled_mode;
 #else
 thread_local int g_last_launches = 0;
 std::atomic<long long> g_total_launches{0};
-std::atomic<int> g_tiled_mode{-1};         // msda_set_tiled_mode(); -1 = take MSDA_B200_TILED from the environment on first use
+std::atomic<int> g_tiled_mode{-1};         // msda_set_tiled_mode(); -1 = take MSDA_B200_TILED (default 0) from the environment on first use
 #endif
 
 static bool tiled_enabled() {
   int m = g_tiled_mode.load(std::memory_order_relaxed);
   if (m < 0) {
     const char* e = std::getenv("MSDA_B200_TILED");
-    m = (e && e[0] == '0') ? 0 : 1;
+    m = (e && e[0] == '1') ? 1 : 0;          // opt-in: measured slower than the direct kernels so far
     g_tiled_mode.store(m, std::memory_order_relaxed);
   }
   return m != 0;
@@ -1024,20 +1029,11 @@ static int tiled_grid(K kernel, int threads, size_t dyn_smem) {
   return per_sm * sms;
 }
 
-static size_t tiled_fwd_smem(int L, int P) {
-  const int LP8 = (L * P + 7) & ~7;
-  return static_cast<size_t>(tiled::kWinRowsCap + 2) * tiled::kRowBytes + static_cast<size_t>(tiled::kQC) * LP8 * 3 * sizeof(uint32_t);
-}
-static size_t tiled_dots_smem(int L, int P) {
-  const int LP8 = (L * P + 7) & ~7;
-  return static_cast<size_t>(tiled::kWinRowsCap + 2) * tiled::kRowBytes + static_cast<size_t>(tiled::kQC) * LP8 * (sizeof(uint32_t) + sizeof(float4));
-}
-
 template <typename T>
 static int launch_fwd_tiled(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
                             const void* loc, const void* attn, void* out, cudaStream_t st) {
   auto kernel = tiled::msda_fwd_tiled_kernel<T>;
-  const size_t smem = tiled_fwd_smem(pr.L, pr.P);
+  const size_t smem = tiled::kFwdSmemBytes;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int grid = tiled_grid(kernel, tiled::kThreadsT, smem);
@@ -1056,7 +1052,7 @@ static int launch_bwd_tiled(const Problem& pr, const void* value, const int64_t*
                             void* gloc, void* gattn, int depth, cudaStream_t st) {
   {
     auto kernel = tiled::msda_bwd_dots_tiled_kernel<T>;
-    const size_t smem = tiled_dots_smem(pr.L, pr.P);
+    const size_t smem = tiled::kDotsSmemBytes;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
     const int grid = tiled_grid(kernel, tiled::kThreadsT, smem);

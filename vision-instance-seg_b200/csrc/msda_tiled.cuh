@@ -42,11 +42,19 @@ constexpr int kMaxL = 8;                   // levels the tiled path supports
 constexpr int kMaxLP = 64;                 // L*P the tiled path supports
 constexpr int kHaloMax = 6;                // pixels of halo per side (3 sigma of N(0, 2^2) px offsets)
 constexpr int kWinRowsCap = 1440;          // window rows (64 bytes each) of one head per CTA
+constexpr int kOvfPts = 16;                // points per chunk whose footprint may leave the windows (private row copies)
+constexpr int kZeroRow = kWinRowsCap;      // rows kZeroRow, kZeroRow + 1: always zero
+constexpr int kOvfRow0 = kWinRowsCap + 2;  // 4 rows (tl, tr, bl, br) per overflow point
+constexpr int kWinRowsAll = kWinRowsCap + 2 + 4 * kOvfPts;
 constexpr int kRowBytes = 64;              // D = 32 channels x 16 bit
 constexpr int kD = 32;
 constexpr int kThreadsT = 256;
-constexpr int kQC = 32;                    // queries per chunk = 8-lane groups per CTA
-constexpr uint32_t kRowFallback = 0xFFFFu; // record marker: footprint outside the window
+constexpr int kGroups = kThreadsT / 8;     // 8-lane groups per CTA
+constexpr int kPF = 4;                     // points per thread per chunk
+constexpr int kChunkPts = kThreadsT * kPF; // record slots per chunk
+constexpr int kQC = 64;                    // queries per chunk (at most; kChunkPts / LP8 if that is smaller)
+constexpr uint32_t kRowFallback = 0xFFFFu; // record marker: footprint outside the windows and no overflow slot left
+constexpr uint32_t kRowsNull = static_cast<uint32_t>(kZeroRow) | (static_cast<uint32_t>(kZeroRow) << 16);
 
 struct Geom {
   int L, lf, halo;
@@ -54,7 +62,7 @@ struct Geom {
   int H[kMaxL], W[kMaxL], start[kMaxL];       // start: level_start_index (value rows)
   int qstart[kMaxL];                          // first query of the level: prefix sums of H*W (queries = pixels)
   int wdx[kMaxL], wdy[kMaxL], base[kMaxL];   // window dims (0: no window) and first window row, per level
-  int rows_total;                             // window rows in use; rows_total, rows_total + 1 are the zero rows
+  int rows_total;                             // window rows in use
   // per tile
   int wx0[kMaxL], wy0[kMaxL];                 // level pixel of window cell (0, 0)
   int qxa[kMaxL], qya[kMaxL], qnx[kMaxL], qny[kMaxL];
@@ -63,12 +71,19 @@ struct Geom {
 
 __device__ __forceinline__ int ceil_div_i(int a, int b) { return (a + b - 1) / b; }
 
+// non-negative 64-bit quotient, through a 32-bit division whenever the operands allow it (64-bit division is a ~100
+// instruction subroutine, and this runs once per tile)
+__device__ __forceinline__ long long div_fast(long long num, long long den) {
+  if (((num | den) >> 32) == 0) return static_cast<long long>(static_cast<uint32_t>(num) / static_cast<uint32_t>(den));
+  return num / den;
+}
+
 // first query column (row) of level extent `wl` that belongs to tile column (row) t of the finest level:
 // membership of query x is floor((x + 0.5) * wf / wl / tile), a monotone map, so the tiles partition every level
 __device__ __forceinline__ int tile_first(long long t, int tile, int wl, int wf) {
   const long long num = 2ll * tile * t * wl - wf;
   if (num <= 0) return 0;
-  const long long v = (num + 2ll * wf - 1) / (2ll * wf);
+  const long long v = div_fast(num + 2ll * wf - 1, 2ll * wf);
   return static_cast<int>(v < wl ? v : wl);
 }
 
@@ -114,29 +129,37 @@ __device__ inline void geom_init(Geom& g, const int64_t* __restrict__ shapes, co
   g.rows_total = base;
 }
 
-// once per work item (thread 0): window origins and the tile's queries
-__device__ inline void geom_tile(Geom& g, int tile) {
+// once per work item (warp 0, lane = level): window origins and the tile's queries
+__device__ __forceinline__ void geom_tile(Geom& g, int tile, int lane) {
   const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
   const int Wf = g.W[g.lf] > 0 ? g.W[g.lf] : 1, Hf = g.H[g.lf] > 0 ? g.H[g.lf] : 1;
-  int off = 0;
-  for (int l = 0; l < g.L; ++l) {
-    g.wx0[l] = static_cast<int>((2ll * kTW * tx * g.W[l] + Wf) / (2ll * Wf)) - g.halo;
-    g.wy0[l] = static_cast<int>((2ll * kTH * ty * g.H[l] + Hf) / (2ll * Hf)) - g.halo;
+  int cnt = 0;
+  if (lane < g.L) {
+    const int l = lane;
+    g.wx0[l] = static_cast<int>(div_fast(2ll * kTW * tx * g.W[l] + Wf, 2ll * Wf)) - g.halo;
+    g.wy0[l] = static_cast<int>(div_fast(2ll * kTH * ty * g.H[l] + Hf, 2ll * Hf)) - g.halo;
     const int xa = tile_first(tx, kTW, g.W[l], Wf), xb = tile_first(tx + 1, kTW, g.W[l], Wf);
     const int ya = tile_first(ty, kTH, g.H[l], Hf), yb = tile_first(ty + 1, kTH, g.H[l], Hf);
     g.qxa[l] = xa; g.qya[l] = ya; g.qnx[l] = xb - xa; g.qny[l] = yb - ya;
-    g.qoff[l] = off;
-    off += (xb - xa) * (yb - ya);
+    cnt = (xb - xa) * (yb - ya);
   }
-  g.qoff[g.L] = off;
+  int incl = cnt;
+#pragma unroll
+  for (int sft = 1; sft < kMaxL; sft <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, sft);
+    if (lane >= sft) incl += t;
+  }
+  if (lane < g.L) g.qoff[lane] = incl - cnt;
+  if (lane == g.L - 1) g.qoff[g.L] = incl;
 }
 
-// global query index of the tile's i-th query (-1 if the shape tensor describes more pixels than there are queries)
+// global query index of the tile's i-th query (-1 past the end, or if the shape tensor describes more pixels than queries)
 __device__ __forceinline__ int tile_query(const Geom& g, int i, int Lq) {
+  if (i >= g.qoff[g.L]) return -1;
   int l = 0;
   while (l + 1 < g.L && i >= g.qoff[l + 1]) ++l;
   const int j = i - g.qoff[l];
-  const int iy = j / g.qnx[l], ix = j - iy * g.qnx[l];
+  const int iy = static_cast<int>(static_cast<uint32_t>(j) / static_cast<uint32_t>(g.qnx[l])), ix = j - iy * g.qnx[l];
   const int q = g.qstart[l] + (g.qya[l] + iy) * g.W[l] + g.qxa[l] + ix;
   return q < Lq ? q : -1;
 }
@@ -156,31 +179,48 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 
-// Fill the CTA's windows with head `head` of image `b`: one warp per window row, 4 lanes per pixel (16 bytes each);
-// cells outside the level are zero-filled, which implements the operator's zero padding.
+// per-level constants a thread keeps in registers
+struct LevelC {
+  float Hf, Wf;
+  int H, W, start, wx0, wy0, wdx, wdy, base;
+};
+__device__ __forceinline__ LevelC level_consts(const Geom& g, int l) {
+  LevelC c;
+  c.H = g.H[l]; c.W = g.W[l]; c.start = g.start[l];
+  c.Hf = static_cast<float>(c.H); c.Wf = static_cast<float>(c.W);
+  c.wx0 = g.wx0[l]; c.wy0 = g.wy0[l]; c.wdx = g.wdx[l]; c.wdy = g.wdy[l]; c.base = g.base[l];
+  return c;
+}
+
+// Fill the CTA's windows with head `head` of image `b`: one warp per window row, 4 lanes per pixel (16 bytes each, so a
+// warp's lanes write 512 contiguous bytes); cells outside the level are zero-filled, which implements the operator's
+// zero padding.  Byte offsets inside one image fit 32 bits (vec_supported).
 template <typename T>
 __device__ __forceinline__ void fill_windows(const Geom& g, uint32_t win, const T* __restrict__ value, int b, int S, int vps,
                                              int head, int warp, int lane, int nwarps) {
   int task0 = 0;
+  const uint32_t pixb = static_cast<uint32_t>(vps) * static_cast<uint32_t>(sizeof(T));
+  const char* img = reinterpret_cast<const char*>(value) + static_cast<size_t>(b) * S * pixb +
+                    static_cast<size_t>(head) * kRowBytes + (lane & 3) * 16;
+  const int lx = lane >> 2;
   for (int l = 0; l < g.L; ++l) {
     const int wdx = g.wdx[l], wdy = g.wdy[l];
-    const int H = g.H[l], W = g.W[l];
-    const char* lvl = reinterpret_cast<const char*>(value) +
-                      (static_cast<size_t>(b) * S + g.start[l]) * static_cast<size_t>(vps) * sizeof(T) + static_cast<size_t>(head) * kRowBytes;
+    const int H = g.H[l], W = g.W[l], wx0 = g.wx0[l], wy0 = g.wy0[l];
+    const char* lvl = img + static_cast<size_t>(g.start[l]) * pixb;
+    const uint32_t dlvl = win + static_cast<uint32_t>(g.base[l]) * kRowBytes + static_cast<uint32_t>(lane) * 16;
     // warp `warp` takes window rows wy with (task0 + wy) % nwarps == warp
     int wy = warp - task0 % nwarps;
     if (wy < 0) wy += nwarps;
     for (; wy < wdy; wy += nwarps) {
-      const int gy = g.wy0[l] + wy;
-      const bool yin = gy >= 0 && gy < H;
-      const uint32_t drow = win + static_cast<uint32_t>(g.base[l] + wy * wdx) * kRowBytes;
-      const char* srow = lvl + static_cast<size_t>(yin ? gy : 0) * W * static_cast<size_t>(vps) * sizeof(T);
-      for (int item = lane; item < wdx * 4; item += 32) {
-        const int x = item >> 2, ch = item & 3;
-        const int gx = g.wx0[l] + x;
-        const bool in = yin && gx >= 0 && gx < W;
-        const char* src = srow + static_cast<size_t>(in ? gx : 0) * static_cast<size_t>(vps) * sizeof(T) + ch * 16;
-        cp_async16_zfill(drow + static_cast<uint32_t>(x) * kRowBytes + ch * 16, in ? src : reinterpret_cast<const char*>(value), in);
+      const int gy = wy0 + wy;
+      const bool yin = static_cast<unsigned>(gy) < static_cast<unsigned>(H);
+      uint32_t dst = dlvl + static_cast<uint32_t>(wy * wdx) * kRowBytes;
+      const char* srow = lvl + static_cast<size_t>(static_cast<uint32_t>(yin ? gy : 0) * static_cast<uint32_t>(W)) * pixb;
+      int gx = wx0 + lx;
+      for (int x = lx; x < wdx; x += 8, gx += 8, dst += 8 * kRowBytes) {
+        const bool in = yin && static_cast<unsigned>(gx) < static_cast<unsigned>(W);
+        const uint32_t off = static_cast<uint32_t>(in ? gx : 0) * pixb;
+        cp_async16_zfill(dst, srow + off, in);
       }
     }
     task0 += wdy;
@@ -203,13 +243,34 @@ __device__ __forceinline__ PointGeo point_geo(float x, float y, float Hf, float 
   return p;
 }
 
-// window rows of the point's top and bottom corner pair, or the fallback marker / the zero rows
-__device__ __forceinline__ uint32_t window_rows(const Geom& g, int l, const PointGeo& p) {
-  if (!p.inside) return static_cast<uint32_t>(g.rows_total) | (static_cast<uint32_t>(g.rows_total) << 16);
-  const int wxr = p.ix - g.wx0[l], wyr = p.iy - g.wy0[l];
-  if (wxr < 0 || wyr < 0 || wxr > g.wdx[l] - 2 || wyr > g.wdy[l] - 2) return kRowFallback | (kRowFallback << 16);
-  const uint32_t top = static_cast<uint32_t>(g.base[l] + wyr * g.wdx[l] + wxr);
-  return top | ((top + static_cast<uint32_t>(g.wdx[l])) << 16);
+// Window rows (top | bottom << 16) of a point's two corner pairs.  A point that fails the gate reads the zero rows.  A
+// footprint that leaves its window gets private copies of its four corner rows in the overflow area (cp.async issued
+// here, completed by the caller's wait + barrier; corners outside the level are zero-filled); when the chunk's overflow
+// slots are used up the marker tells the gather loop to fetch from global memory itself.
+template <typename T>
+__device__ __forceinline__ uint32_t resolve_rows(const PointGeo& p, const LevelC& c, uint32_t win, const T* __restrict__ img,
+                                                 int vps, int head, int* s_ovf) {
+  if (!p.inside) return kRowsNull;
+  const int wxr = p.ix - c.wx0, wyr = p.iy - c.wy0;
+  if (wxr >= 0 && wyr >= 0 && wxr <= c.wdx - 2 && wyr <= c.wdy - 2) {
+    const uint32_t top = static_cast<uint32_t>(c.base + wyr * c.wdx + wxr);
+    return top | ((top + static_cast<uint32_t>(c.wdx)) << 16);
+  }
+  const int slot = atomicAdd(s_ovf, 1);
+  if (slot >= kOvfPts) return kRowFallback | (kRowFallback << 16);
+  const uint32_t r0 = static_cast<uint32_t>(kOvfRow0 + 4 * slot);
+  const size_t pix_bytes = static_cast<size_t>(vps) * sizeof(T);
+  const char* base = reinterpret_cast<const char*>(img) + static_cast<size_t>(head) * kRowBytes;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = p.ix + (k & 1), y = p.iy + (k >> 1);
+    const bool in = static_cast<unsigned>(x) < static_cast<unsigned>(c.W) && static_cast<unsigned>(y) < static_cast<unsigned>(c.H);
+    const char* src = in ? base + (static_cast<size_t>(c.start) + static_cast<size_t>(y) * c.W + x) * pix_bytes
+                         : reinterpret_cast<const char*>(img);
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) cp_async16_zfill(win + (r0 + k) * kRowBytes + ch * 16, src + ch * 16, in);
+  }
+  return r0 | ((r0 + 2) << 16);
 }
 
 // Slow path: the 16 bytes of this lane's pixel (side s: left / right column, chunk c) of the top and bottom row of a
@@ -230,10 +291,30 @@ __device__ __forceinline__ void fetch_global_pair(const T* __restrict__ img, int
 
 __device__ __forceinline__ int round_up8(int v) { return (v + 7) & ~7; }
 
+// How the kChunkPts record slots of a chunk map to threads: slot = qi * LP8 + lp, thread tid handles slots
+// tid + it * kThreadsT.  When LP8 divides the CTA size a thread's lp (hence its level) never changes.
+struct SlotMap {
+  int LP, LP8, qc;           // points per pair, padded, queries per chunk
+  bool fixed;
+  int lp_fixed, qi_fixed, qstep;
+  __device__ __forceinline__ void init(int L, int P, int tid) {
+    LP = L * P; LP8 = round_up8(LP);
+    qc = min(kQC, kChunkPts / LP8);
+    fixed = (kThreadsT % LP8) == 0;
+    lp_fixed = tid % LP8; qi_fixed = tid / LP8; qstep = kThreadsT / LP8;
+  }
+  __device__ __forceinline__ void slot(int tid, int it, int& qi, int& lp) const {
+    if (fixed) { qi = qi_fixed + it * qstep; lp = lp_fixed; }
+    else { const int idx = tid + it * kThreadsT; qi = idx / LP8; lp = idx - qi * LP8; }
+  }
+};
+
 // =====================================================================================================
 // Forward
 // =====================================================================================================
-// shared memory: windows [(cap + 2) rows x 64 B] | rows [kQC][LP8] u32 | weights [kQC][2 sides][LP8] u32
+// shared memory: windows [kWinRowsAll x 64 B] | rows [kChunkPts] u32 | weights [2 sides][kChunkPts] u32
+constexpr size_t kFwdSmemBytes = static_cast<size_t>(kWinRowsAll) * kRowBytes + static_cast<size_t>(kChunkPts) * 3 * 4;
+
 template <typename T>
 __global__ void __launch_bounds__(kThreadsT, 2)
 msda_fwd_tiled_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
@@ -241,116 +322,148 @@ msda_fwd_tiled_kernel(const T* __restrict__ value, const int64_t* __restrict__ s
                       int N, int S, int M, int Lq, int L, int P, int vps) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ Geom g;
-  __shared__ int s_qid[kQC];
+  __shared__ int s_qid[2][kQC];
+  __shared__ int s_ovf;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int LP = L * P, LP8 = round_up8(LP);
+  SlotMap sm;
+  sm.init(L, P, tid);
+  const int LP = sm.LP, LP8 = sm.LP8;
   unsigned char* win_ptr = smem_raw;
-  uint32_t* s_rows = reinterpret_cast<uint32_t*>(smem_raw + static_cast<size_t>(kWinRowsCap + 2) * kRowBytes);
-  uint32_t* s_wts = s_rows + kQC * LP8;
+  uint32_t* s_rows = reinterpret_cast<uint32_t*>(smem_raw + static_cast<size_t>(kWinRowsAll) * kRowBytes);
+  uint32_t* s_wts = s_rows + kChunkPts;              // [side][slot]
   const uint32_t win = smem_u32(win_ptr);
 
-  if (tid == 0) geom_init(g, shapes, lsi, L, kWinRowsCap);
+  if (tid == 0) { geom_init(g, shapes, lsi, L, kWinRowsCap); s_ovf = 0; }
+  if (tid < 2 * kRowBytes / 16)                      // the zero rows: written once, never overwritten
+    reinterpret_cast<uint4*>(win_ptr + static_cast<size_t>(kZeroRow) * kRowBytes)[tid] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
-  // zero rows (read by points that fail the gate and by padding slots); written once, never overwritten
-  if (tid < 2 * kRowBytes / 16)
-    reinterpret_cast<uint4*>(win_ptr + static_cast<size_t>(g.rows_total) * kRowBytes)[tid] = make_uint4(0u, 0u, 0u, 0u);
   const int tiles = g.tiles_x * g.tiles_y;
   const long long total = static_cast<long long>(N) * tiles * M;
   const float inv_p = 1.0f / static_cast<float>(P);
-  const int grp = tid >> 3;                 // 8-lane group = one query of the chunk
+  const int grp = tid >> 3;                          // 8-lane group
   const int s = (lane >> 2) & 1, c = lane & 3;
   const uint32_t lane_off = static_cast<uint32_t>(s * kRowBytes + c * 16);
+  const float nanf_ = __int_as_float(0x7fc00000);
 
   for (long long work = blockIdx.x; work < total; work += gridDim.x) {
     const int head = static_cast<int>(work % M);
     const int tile = static_cast<int>((work / M) % tiles);
     const int b = static_cast<int>(work / (static_cast<long long>(M) * tiles));
-    __syncthreads();                        // the previous work item no longer reads the windows / geometry
-    if (tid == 0) geom_tile(g, tile);
+    __syncthreads();                                 // the previous work item no longer reads windows / geometry / qids
+    if (warp == 0) geom_tile(g, tile, lane);
     __syncthreads();
     fill_windows<T>(g, win, value, b, S, vps, head, warp, lane, kThreadsT / 32);
     cp_async_commit();
     const int nq = g.qoff[L];
     const T* img = value + static_cast<size_t>(b) * S * static_cast<size_t>(vps);
+    if (tid < kQC) s_qid[0][tid] = tid < sm.qc ? tile_query(g, tid, Lq) : -1;
+    LevelC lc = level_consts(g, level_of(min(sm.lp_fixed, LP - 1), inv_p));
+    __syncthreads();
 
-    for (int chunk0 = 0; chunk0 < nq; chunk0 += kQC) {
-      const int ncq = min(kQC, nq - chunk0);
-      if (chunk0 > 0) __syncthreads();      // records of the previous chunk are no longer read
-      if (tid < kQC) s_qid[tid] = tid < ncq ? tile_query(g, chunk0 + tid, Lq) : -1;
-      __syncthreads();
-      // ---- phase A: lane = point.  window rows + packed 16-bit weights (top | bottom) per side ----
-      for (int idx = tid; idx < kQC * LP8; idx += kThreadsT) {
-        const int qi = idx / LP8, lp = idx - qi * LP8;
-        const int q = s_qid[qi];
-        uint32_t rows = static_cast<uint32_t>(g.rows_total) | (static_cast<uint32_t>(g.rows_total) << 16);
-        uint32_t wl = 0u, wr = 0u;
+    float2 pxy[kPF];
+    float pa[kPF];
+    // raw sampling locations / weights of a chunk's points, one slot per (thread, it); NaN marks an empty slot
+    auto prefetch = [&](const int* qid) {
+#pragma unroll
+      for (int it = 0; it < kPF; ++it) {
+        int qi, lp;
+        sm.slot(tid, it, qi, lp);
+        const int q = qi < sm.qc ? qid[qi] : -1;
+        pxy[it] = make_float2(nanf_, nanf_);
+        pa[it] = 0.f;
         if (q >= 0 && lp < LP) {
           const size_t pair = (static_cast<size_t>(b) * Lq + q) * M + head;
-          const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + pair * LP + lp);
-          const float a = __ldg(attn + pair * LP + lp);
-          const int l = level_of(lp, inv_p);
-          const PointGeo pg = point_geo(xy.x, xy.y, static_cast<float>(g.H[l]), static_cast<float>(g.W[l]));
-          rows = window_rows(g, l, pg);
-          if (pg.inside) {
-            const float ah = (1.f - pg.lh) * a, al = pg.lh * a;
-            const float hw = 1.f - pg.lw;
-            wl = pack_weight_pair<T>(ah * hw, al * hw);
-            wr = pack_weight_pair<T>(ah * pg.lw, al * pg.lw);
-          }
+          pxy[it] = __ldg(reinterpret_cast<const float2*>(loc) + pair * LP + lp);
+          pa[it] = __ldg(attn + pair * LP + lp);
         }
-        s_rows[qi * LP8 + lp] = rows;
-        s_wts[(qi * 2 + 0) * LP8 + lp] = wl;
-        s_wts[(qi * 2 + 1) * LP8 + lp] = wr;
       }
-      if (chunk0 == 0) cp_async_wait_all();
-      __syncthreads();
+    };
+    prefetch(s_qid[0]);
+
+    int buf = 0;
+    for (int chunk0 = 0; chunk0 < nq; chunk0 += sm.qc, buf ^= 1) {
+      // ---- phase A: lane = point.  window rows + packed 16-bit weights (top | bottom) per side ----
+#pragma unroll
+      for (int it = 0; it < kPF; ++it) {
+        int qi, lp;
+        sm.slot(tid, it, qi, lp);
+        if (!sm.fixed) lc = level_consts(g, level_of(min(lp, LP - 1), inv_p));
+        const PointGeo pg = point_geo(pxy[it].x, pxy[it].y, lc.Hf, lc.Wf);
+        const uint32_t rows = resolve_rows<T>(pg, lc, win, img, vps, head, &s_ovf);
+        uint32_t wl = 0u, wr = 0u;
+        if (pg.inside) {
+          const float ah = (1.f - pg.lh) * pa[it], al = pg.lh * pa[it];
+          const float hw = 1.f - pg.lw;
+          wl = pack_weight_pair<T>(ah * hw, al * hw);
+          wr = pack_weight_pair<T>(ah * pg.lw, al * pg.lw);
+        }
+        const int slot = qi * LP8 + lp;
+        if (slot < kChunkPts) {
+          s_rows[slot] = rows;
+          s_wts[slot] = wl;
+          s_wts[kChunkPts + slot] = wr;
+        }
+      }
+      const bool more = chunk0 + sm.qc < nq;
+      if (more && tid < kQC) s_qid[buf ^ 1][tid] = tid < sm.qc ? tile_query(g, chunk0 + sm.qc + tid, Lq) : -1;
+      cp_async_commit();
+      cp_async_wait_all();
+      __syncthreads();                               // records, windows, overflow rows and the next chunk's query ids are visible
+      if (tid == 0) s_ovf = 0;                       // slots of this chunk are assigned; nobody touches the counter until the next phase A
+      if (more) prefetch(s_qid[buf ^ 1]);            // in flight during the gather
+
       // ---- gather: 8 lanes per query; lanes 0-3 the left pixel of every corner pair, lanes 4-7 the right one.
-      //      Groups without a query (last chunk of a tile) run the same code on the zero rows: the shuffles below are
-      //      full-mask ----
-      const int q = s_qid[grp];
-      const bool active = q >= 0;
-      float acc[8];
+      //      Groups without a query run the same code on the zero rows: the shuffles below are full-mask ----
+      const int ncq = min(sm.qc, nq - chunk0);
+      for (int r0 = 0; r0 < ncq; r0 += kGroups) {     // CTA-uniform trip count: every lane runs the full-mask shuffles
+        const int qi = (r0 + grp < sm.qc) ? r0 + grp : 0;   // groups past the chunk shadow query 0 (read-only)
+        const int q = (r0 + grp < sm.qc) ? s_qid[buf][qi] : -1;
+        const bool active = q >= 0;
+        float acc[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      const uint32_t* rrow = s_rows + grp * LP8;
-      const uint32_t* wrow = s_wts + (grp * 2 + s) * LP8;
-      const size_t pair = (static_cast<size_t>(b) * Lq + (active ? q : 0)) * M + head;
-      for (int lp0 = 0; lp0 < LP8; lp0 += 4) {
-        const uint4 r4 = *reinterpret_cast<const uint4*>(rrow + lp0);
-        const uint4 w4 = *reinterpret_cast<const uint4*>(wrow + lp0);
-        const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
-        const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
-        const bool slow = ((r4.x & 0xFFFFu) == kRowFallback) | ((r4.y & 0xFFFFu) == kRowFallback) |
-                          ((r4.z & 0xFFFFu) == kRowFallback) | ((r4.w & 0xFFFFu) == kRowFallback);
-        if (!slow) {
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        const uint32_t* rrow = s_rows + qi * LP8;
+        const uint32_t* wrow = s_wts + s * kChunkPts + qi * LP8;
+        const size_t pair = (static_cast<size_t>(b) * Lq + (active ? q : 0)) * M + head;
+        for (int lp0 = 0; lp0 < LP8; lp0 += 4) {
+          const uint4 r4 = *reinterpret_cast<const uint4*>(rrow + lp0);
+          const uint4 w4 = *reinterpret_cast<const uint4*>(wrow + lp0);
+          const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+          const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
+          const bool slow = ((r4.x & 0xFFFFu) == kRowFallback) | ((r4.y & 0xFFFFu) == kRowFallback) |
+                            ((r4.z & 0xFFFFu) == kRowFallback) | ((r4.w & 0xFFFFu) == kRowFallback);
+          if (!slow) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 ut = lds128(win + (rr[j] & 0xFFFFu) * kRowBytes + lane_off);
-            const uint4 ub = lds128(win + (rr[j] >> 16) * kRowBytes + lane_off);
-            axpy16_packed<T>(acc, ut, ww[j], false);
-            axpy16_packed<T>(acc, ub, ww[j], true);
-          }
-        } else {                                  // group-uniform: some point of the four left its window
-          for (int j = 0; j < 4; ++j) {
-            uint4 ut, ub;
-            if ((rr[j] & 0xFFFFu) == kRowFallback) {
-              const int lp = lp0 + j;
-              const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + pair * LP + lp);
-              const int l = level_of(lp, inv_p);
-              const PointGeo pg = point_geo(xy.x, xy.y, static_cast<float>(g.H[l]), static_cast<float>(g.W[l]));
-              fetch_global_pair<T>(img, g.start[l], g.H[l], g.W[l], vps, head, pg.ix, pg.iy, s, c, ut, ub);
-            } else {
-              ut = lds128(win + (rr[j] & 0xFFFFu) * kRowBytes + lane_off);
-              ub = lds128(win + (rr[j] >> 16) * kRowBytes + lane_off);
+            for (int j = 0; j < 4; ++j) {
+              const uint4 ut = lds128(win + (rr[j] & 0xFFFFu) * kRowBytes + lane_off);
+              const uint4 ub = lds128(win + (rr[j] >> 16) * kRowBytes + lane_off);
+              axpy16_packed<T>(acc, ut, ww[j], false);
+              axpy16_packed<T>(acc, ub, ww[j], true);
             }
-            axpy16_packed<T>(acc, ut, ww[j], false);
-            axpy16_packed<T>(acc, ub, ww[j], true);
+          } else {                                   // group-uniform and rare: the chunk ran out of overflow slots
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 ut, ub;
+              if ((rr[j] & 0xFFFFu) == kRowFallback) {
+                const int lp = lp0 + j;
+                const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + pair * LP + lp);
+                const int l = level_of(lp, inv_p);
+                const PointGeo pg = point_geo(xy.x, xy.y, static_cast<float>(g.H[l]), static_cast<float>(g.W[l]));
+                fetch_global_pair<T>(img, g.start[l], g.H[l], g.W[l], vps, head, pg.ix, pg.iy, s, c, ut, ub);
+              } else {
+                ut = lds128(win + (rr[j] & 0xFFFFu) * kRowBytes + lane_off);
+                ub = lds128(win + (rr[j] >> 16) * kRowBytes + lane_off);
+              }
+              axpy16_packed<T>(acc, ut, ww[j], false);
+              axpy16_packed<T>(acc, ub, ww[j], true);
+            }
           }
         }
-      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 4);
-      if (active && s == 0) __stcs(reinterpret_cast<uint4*>(out + pair * kD + c * 8), pack16<T>(acc));
+        for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 4);
+        if (active && s == 0) __stcs(reinterpret_cast<uint4*>(out + pair * kD + c * 8), pack16<T>(acc));
+      }
+      __syncthreads();                               // records / overflow rows of this chunk are no longer read
     }
   }
 }
@@ -358,7 +471,17 @@ msda_fwd_tiled_kernel(const T* __restrict__ value, const int64_t* __restrict__ s
 // =====================================================================================================
 // Backward, part 1: grad_sampling_loc, grad_attn_weight (and max|grad_out| for the fp16 scale of part 2)
 // =====================================================================================================
-// shared memory: windows | rows [kQC][LP8] u32 | params [kQC][LP8] float4 (lw, lh, a*W, a*H)
+// Gather mapping: the 8 lanes of a group work on two points at a time, one lane per corner ROW (64 bytes = the whole
+// head slice), so every lane finishes its corner's <value, grad_out> alone and no channel reduction is needed.  A lane
+// reads its row as four 16-byte chunks in the rotated order (c0 + k) mod 4, c0 = 2*point + (corner >> 1): the two x
+// neighbours of a footprint always differ in 64-byte parity and rows of the same parity get different c0, so the 8
+// lanes of a quarter warp hit 8 different bank groups (conflict-free) whatever the window pitch.  After four such
+// steps (8 points) a 4x4 transpose inside each quad (4 shuffles) leaves lane (point, corner) with all four corner dots
+// of point 2*corner + point, whose three gradients it then writes.
+// shared memory: windows | rows [kChunkPts] u32 | lw, lh [kChunkPts] float each | grad_out rows [kQC][64 B]
+constexpr size_t kDotsSmemBytes = static_cast<size_t>(kWinRowsAll) * kRowBytes + static_cast<size_t>(kChunkPts) * 3 * 4 +
+                                  static_cast<size_t>(kQC) * kRowBytes;
+
 template <typename T>
 __global__ void __launch_bounds__(kThreadsT, 2)
 msda_bwd_dots_tiled_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
@@ -367,24 +490,35 @@ msda_bwd_dots_tiled_kernel(const T* __restrict__ value, const int64_t* __restric
                            int N, int S, int M, int Lq, int L, int P, int vps) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ Geom g;
-  __shared__ int s_qid[kQC];
+  __shared__ int s_qid[2][kQC];
+  __shared__ int s_ovf;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int LP = L * P, LP8 = round_up8(LP);
+  SlotMap sm;
+  sm.init(L, P, tid);
+  const int LP = sm.LP, LP8 = sm.LP8;
   unsigned char* win_ptr = smem_raw;
-  uint32_t* s_rows = reinterpret_cast<uint32_t*>(smem_raw + static_cast<size_t>(kWinRowsCap + 2) * kRowBytes);
-  float4* s_par = reinterpret_cast<float4*>(s_rows + kQC * LP8);
+  uint32_t* s_rows = reinterpret_cast<uint32_t*>(smem_raw + static_cast<size_t>(kWinRowsAll) * kRowBytes);
+  float* s_lw = reinterpret_cast<float*>(s_rows + kChunkPts);
+  float* s_lh = s_lw + kChunkPts;
+  unsigned char* s_go = reinterpret_cast<unsigned char*>(s_lh + kChunkPts);
   const uint32_t win = smem_u32(win_ptr);
+  const uint32_t go_base = smem_u32(s_go);
 
-  if (tid == 0) geom_init(g, shapes, lsi, L, kWinRowsCap);
-  __syncthreads();
+  if (tid == 0) { geom_init(g, shapes, lsi, L, kWinRowsCap); s_ovf = 0; }
   if (tid < 2 * kRowBytes / 16)
-    reinterpret_cast<uint4*>(win_ptr + static_cast<size_t>(g.rows_total) * kRowBytes)[tid] = make_uint4(0u, 0u, 0u, 0u);
+    reinterpret_cast<uint4*>(win_ptr + static_cast<size_t>(kZeroRow) * kRowBytes)[tid] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
   const int tiles = g.tiles_x * g.tiles_y;
   const long long total = static_cast<long long>(N) * tiles * M;
   const float inv_p = 1.0f / static_cast<float>(P);
   const int grp = tid >> 3;
-  const int s = (lane >> 2) & 1, c = lane & 3;
-  const uint32_t lane_off = static_cast<uint32_t>(s * kRowBytes + c * 16);
+  const int pt = (lane >> 2) & 1, cr = lane & 3;            // point of the pair, corner (bit 0: right, bit 1: bottom)
+  const int c0 = 2 * pt + (cr >> 1);
+  const uint32_t rsh = (cr & 2) ? 16u : 0u;                 // which half of the rows word holds my row pair
+  uint32_t coff[4];                                         // byte offsets of my four chunks inside the corner pair
+#pragma unroll
+  for (int k = 0; k < 4; ++k) coff[k] = static_cast<uint32_t>(((c0 + k) & 3) * 16 + (cr & 1) * kRowBytes);
+  const float nanf_ = __int_as_float(0x7fc00000);
   float go_max = 0.f;
 
   for (long long work = blockIdx.x; work < total; work += gridDim.x) {
@@ -392,122 +526,137 @@ msda_bwd_dots_tiled_kernel(const T* __restrict__ value, const int64_t* __restric
     const int tile = static_cast<int>((work / M) % tiles);
     const int b = static_cast<int>(work / (static_cast<long long>(M) * tiles));
     __syncthreads();
-    if (tid == 0) geom_tile(g, tile);
+    if (warp == 0) geom_tile(g, tile, lane);
     __syncthreads();
     fill_windows<T>(g, win, value, b, S, vps, head, warp, lane, kThreadsT / 32);
     cp_async_commit();
     const int nq = g.qoff[L];
     const T* img = value + static_cast<size_t>(b) * S * static_cast<size_t>(vps);
+    if (tid < kQC) s_qid[0][tid] = tid < sm.qc ? tile_query(g, tid, Lq) : -1;
+    LevelC lc = level_consts(g, level_of(min(sm.lp_fixed, LP - 1), inv_p));
+    __syncthreads();
 
-    for (int chunk0 = 0; chunk0 < nq; chunk0 += kQC) {
-      const int ncq = min(kQC, nq - chunk0);
-      if (chunk0 > 0) __syncthreads();
-      if (tid < kQC) s_qid[tid] = tid < ncq ? tile_query(g, chunk0 + tid, Lq) : -1;
-      __syncthreads();
-      for (int idx = tid; idx < kQC * LP8; idx += kThreadsT) {
-        const int qi = idx / LP8, lp = idx - qi * LP8;
-        const int q = s_qid[qi];
-        uint32_t rows = static_cast<uint32_t>(g.rows_total) | (static_cast<uint32_t>(g.rows_total) << 16);
-        float4 par = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 pxy[kPF];
+    auto prefetch = [&](const int* qid) {
+#pragma unroll
+      for (int it = 0; it < kPF; ++it) {
+        int qi, lp;
+        sm.slot(tid, it, qi, lp);
+        const int q = qi < sm.qc ? qid[qi] : -1;
+        pxy[it] = make_float2(nanf_, nanf_);
         if (q >= 0 && lp < LP) {
           const size_t pair = (static_cast<size_t>(b) * Lq + q) * M + head;
-          const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + pair * LP + lp);
-          const float a = __ldg(attn + pair * LP + lp);
-          const int l = level_of(lp, inv_p);
-          const float Hf = static_cast<float>(g.H[l]), Wf = static_cast<float>(g.W[l]);
-          const PointGeo pg = point_geo(xy.x, xy.y, Hf, Wf);
-          rows = window_rows(g, l, pg);
-          if (pg.inside) par = make_float4(pg.lw, pg.lh, Wf * a, Hf * a);
+          pxy[it] = __ldg(reinterpret_cast<const float2*>(loc) + pair * LP + lp);
         }
-        s_rows[qi * LP8 + lp] = rows;
-        s_par[qi * LP8 + lp] = par;
       }
-      if (chunk0 == 0) cp_async_wait_all();
-      __syncthreads();
+    };
+    prefetch(s_qid[0]);
 
-      const int q = s_qid[grp];
-      const bool active = q >= 0;
-      const size_t pair = (static_cast<size_t>(b) * Lq + (active ? q : 0)) * M + head;
-      uint4 go_raw = make_uint4(0u, 0u, 0u, 0u);
-      if (active) {
-        go_raw = ldg16(grad_out + pair * kD + c * 8);
+    int buf = 0;
+    for (int chunk0 = 0; chunk0 < nq; chunk0 += sm.qc, buf ^= 1) {
+      // ---- phase A: lane = point.  window rows + fractions; this chunk's grad_out rows ----
+#pragma unroll
+      for (int it = 0; it < kPF; ++it) {
+        int qi, lp;
+        sm.slot(tid, it, qi, lp);
+        if (!sm.fixed) lc = level_consts(g, level_of(min(lp, LP - 1), inv_p));
+        const PointGeo pg = point_geo(pxy[it].x, pxy[it].y, lc.Hf, lc.Wf);
+        const uint32_t rows = resolve_rows<T>(pg, lc, win, img, vps, head, &s_ovf);
+        const int slot = qi * LP8 + lp;
+        if (slot < kChunkPts) {
+          s_rows[slot] = rows;
+          s_lw[slot] = pg.inside ? pg.lw : nanf_;      // NaN: the point fails the gate, its gradients are zero
+          s_lh[slot] = pg.lh;
+        }
+      }
+      if (tid < kQC * 4) {
+        const int qi = tid >> 2, ch = tid & 3;
+        const int q = qi < sm.qc ? s_qid[buf][qi] : -1;
+        const size_t pair = (static_cast<size_t>(b) * Lq + (q >= 0 ? q : 0)) * M + head;
+        cp_async16_zfill(go_base + static_cast<uint32_t>(qi * kRowBytes + ch * 16), grad_out + pair * kD + ch * 8, q >= 0);
+      }
+      const bool more = chunk0 + sm.qc < nq;
+      if (more && tid < kQC) s_qid[buf ^ 1][tid] = tid < sm.qc ? tile_query(g, chunk0 + sm.qc + tid, Lq) : -1;
+      cp_async_commit();
+      cp_async_wait_all();
+      __syncthreads();
+      if (tid == 0) s_ovf = 0;
+      if (more) prefetch(s_qid[buf ^ 1]);
+      if (tid < kQC * 4) {                                 // max|grad_out| over the rows this chunk staged
         float f[8];
-        unpack16<T>(go_raw, f);
+        unpack16<T>(*reinterpret_cast<const uint4*>(s_go + tid * 16), f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) go_max = fmaxf(go_max, fabsf(f[i]));
       }
-      const uint32_t* rrow = s_rows + grp * LP8;
-      const float4* prow = s_par + grp * LP8;
-      for (int lp0 = 0; lp0 < LP8; lp0 += 8) {
-        float d[8][2];                          // per point: <value, grad_out> over this lane's 8 channels, top / bottom row
+
+      const int ncq = min(sm.qc, nq - chunk0);
+      for (int r0 = 0; r0 < ncq; r0 += kGroups) {
+        const int qi = (r0 + grp < sm.qc) ? r0 + grp : 0;
+        const int q = (r0 + grp < sm.qc) ? s_qid[buf][qi] : -1;
+        const bool active = q >= 0;
+        const size_t pair = (static_cast<size_t>(b) * Lq + (active ? q : 0)) * M + head;
+        uint4 gor[4];                                      // the pair's grad_out row, chunks in my rotated order
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint4 r4 = *reinterpret_cast<const uint4*>(rrow + lp0 + 4 * half);
-          const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+        for (int k = 0; k < 4; ++k) gor[k] = lds128(go_base + static_cast<uint32_t>(qi * kRowBytes + ((c0 + k) & 3) * 16));
+        const uint32_t* rrow = s_rows + qi * LP8;
+        for (int lp0 = 0; lp0 < LP8; lp0 += 8) {
+          const int lp = lp0 + 2 * cr + pt;               // the point this lane owns after the transpose
+          float a_own = 0.f;
+          if (active && lp < LP) a_own = __ldg(attn + pair * LP + lp);
+          const uint4 ra = *reinterpret_cast<const uint4*>(rrow + lp0);
+          const uint4 rb = *reinterpret_cast<const uint4*>(rrow + lp0 + 4);
+          const uint32_t rw[4] = {pt ? ra.y : ra.x, pt ? ra.w : ra.z, pt ? rb.y : rb.x, pt ? rb.w : rb.z};
+          float d[4];                                      // my corner's dot for points lp0 + 2i + pt
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 ut, ub;
-            if ((rr[j] & 0xFFFFu) == kRowFallback) {     // group-uniform
-              const int lp = lp0 + 4 * half + j;
-              const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + pair * LP + lp);
-              const int l = level_of(lp, inv_p);
+          for (int i = 0; i < 4; ++i) {
+            float acc = 0.f;
+            if ((rw[i] & 0xFFFFu) != kRowFallback) {
+              const uint32_t addr = win + ((rw[i] >> rsh) & 0xFFFFu) * kRowBytes;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) acc = dot16<T>(lds128(addr + coff[k]), gor[k], acc);
+            } else {                                       // rare: no overflow slot was left for this point
+              const int lpi = lp0 + 2 * i + pt;
+              const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + pair * LP + lpi);
+              const int l = level_of(lpi, inv_p);
               const PointGeo pg = point_geo(xy.x, xy.y, static_cast<float>(g.H[l]), static_cast<float>(g.W[l]));
-              fetch_global_pair<T>(img, g.start[l], g.H[l], g.W[l], vps, head, pg.ix, pg.iy, s, c, ut, ub);
-            } else {
-              ut = lds128(win + (rr[j] & 0xFFFFu) * kRowBytes + lane_off);
-              ub = lds128(win + (rr[j] >> 16) * kRowBytes + lane_off);
+              const int x = pg.ix + (cr & 1), y = pg.iy + (cr >> 1);
+              if (static_cast<unsigned>(x) < static_cast<unsigned>(g.W[l]) && static_cast<unsigned>(y) < static_cast<unsigned>(g.H[l])) {
+                const char* row = reinterpret_cast<const char*>(img) + static_cast<size_t>(head) * kRowBytes +
+                                  (static_cast<size_t>(g.start[l]) + static_cast<size_t>(y) * g.W[l] + x) * static_cast<size_t>(vps) * sizeof(T);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc = dot16<T>(ldg16(row + ((c0 + k) & 3) * 16), gor[k], acc);
+              }
             }
-            d[4 * half + j][0] = dot16<T>(ut, go_raw, 0.f);
-            d[4 * half + j][1] = dot16<T>(ub, go_raw, 0.f);
+            d[i] = acc;
           }
-        }
-        // reduce-scatter over the 4 channel lanes of a side: lane c ends with the side totals of points 2c, 2c+1
-        {
-          const bool up = (c & 2) != 0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              const float keep = up ? d[j + 4][r] : d[j][r];
-              const float send = up ? d[j][r] : d[j + 4][r];
-              d[j][r] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
+          // 4x4 transpose inside the quad: lane `cr` ends with the four corner dots of point i = cr
+          const bool oddc = (cr & 1) != 0, bot = (cr & 2) != 0;
+          const float rA0 = __shfl_xor_sync(0xffffffffu, oddc ? d[0] : d[1], 1);
+          const float rA1 = __shfl_xor_sync(0xffffffffu, oddc ? d[2] : d[3], 1);
+          const float kA0 = oddc ? d[1] : d[0], kA1 = oddc ? d[3] : d[2];
+          const float a_lo = oddc ? rA0 : kA0, a_hi = oddc ? kA0 : rA0;       // point (cr & 1), my corner pair (x, x+1)
+          const float b_lo = oddc ? rA1 : kA1, b_hi = oddc ? kA1 : rA1;       // point 2 + (cr & 1)
+          const float rB_lo = __shfl_xor_sync(0xffffffffu, bot ? a_lo : b_lo, 2);
+          const float rB_hi = __shfl_xor_sync(0xffffffffu, bot ? a_hi : b_hi, 2);
+          const float kB_lo = bot ? b_lo : a_lo, kB_hi = bot ? b_hi : a_hi;
+          const float d00 = bot ? rB_lo : kB_lo, d01 = bot ? rB_hi : kB_hi;
+          const float d10 = bot ? kB_lo : rB_lo, d11 = bot ? kB_hi : rB_hi;
+          if (active && lp < LP) {
+            const int slot = qi * LP8 + lp;
+            float lw = s_lw[slot], lh = s_lh[slot];
+            float a = a_own;
+            if (!(lw == lw)) { lw = 0.f; lh = 0.f; a = 0.f; }   // gate failed: upstream skips the point
+            const int l = level_of(lp, inv_p);
+            const float hw = 1.f - lw, hh = 1.f - lh;
+            const float ga = hh * (hw * d00 + lw * d01) + lh * (hw * d10 + lw * d11);
+            const float gx = static_cast<float>(g.W[l]) * a * (hh * (d01 - d00) + lh * (d11 - d10));
+            const float gy = static_cast<float>(g.H[l]) * a * (hw * (d10 - d00) + lw * (d11 - d01));
+            __stcs(reinterpret_cast<float2*>(grad_loc) + pair * LP + lp, make_float2(gx, gy));
+            __stcs(grad_attn + pair * LP + lp, ga);
           }
-        }
-        {
-          const bool up = (c & 1) != 0;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              const float keep = up ? d[j + 2][r] : d[j][r];
-              const float send = up ? d[j][r] : d[j + 2][r];
-              d[j][r] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-            }
-          }
-        }
-        // exchange between the sides: lane (s, c) ends with all four corner dots of point 2c + s
-        float dt_own, db_own, dt_oth, db_oth;
-        {
-          const float send_t = s ? d[0][0] : d[1][0], send_b = s ? d[0][1] : d[1][1];
-          dt_own = s ? d[1][0] : d[0][0];
-          db_own = s ? d[1][1] : d[0][1];
-          dt_oth = __shfl_xor_sync(0xffffffffu, send_t, 4);
-          db_oth = __shfl_xor_sync(0xffffffffu, send_b, 4);
-        }
-        const float d00 = s ? dt_oth : dt_own, d01 = s ? dt_own : dt_oth;
-        const float d10 = s ? db_oth : db_own, d11 = s ? db_own : db_oth;
-        const int lp = lp0 + 2 * c + s;
-        if (active && lp < LP) {
-          const float4 par = prow[lp];
-          const float lw = par.x, lh = par.y, hw = 1.f - lw, hh = 1.f - lh;
-          const float ga = hh * (hw * d00 + lw * d01) + lh * (hw * d10 + lw * d11);
-          const float gx = par.z * (hh * (d01 - d00) + lh * (d11 - d10));
-          const float gy = par.w * (hw * (d10 - d00) + lw * (d11 - d01));
-          __stcs(reinterpret_cast<float2*>(grad_loc) + pair * LP + lp, make_float2(gx, gy));
-          __stcs(grad_attn + pair * LP + lp, ga);
         }
       }
+      __syncthreads();
     }
   }
   if (ctrl != nullptr) {
@@ -521,15 +670,28 @@ msda_bwd_dots_tiled_kernel(const T* __restrict__ value, const int64_t* __restric
 // Backward, part 2: grad_value by counting sort + segmented sums (no read-modify-write in shared memory)
 // =====================================================================================================
 constexpr int kScThreads = 256;
-constexpr int kScIters = 4;                       // points per thread per level round
+constexpr int kScIters = 3;                       // points per thread per level round
 constexpr int kScPoints = kScThreads * kScIters;  // points of one level handled per round
 constexpr int kScEntries = kScPoints * 4;         // corner rows per round
 constexpr int kScQueries = 256;                   // queries per round (8-bit local index)
+constexpr int kScMaxRun = 64;                     // adds per fp16 register accumulator before it is flushed
 
-// shared memory: go2 [kScQueries][2][64 B] | entries [kScEntries] uint2 | cnt [kWinRowsCap + 1] u32 | qid [kScQueries]
+// shared memory: go2 [kScQueries][2][64 B] | entries [kScEntries] uint2 | cnt [kWinRowsCap + 1] u32 | dst [kWinRowsCap] u32 |
+//                qid [kScQueries]
 constexpr size_t kScSmemBytes = static_cast<size_t>(kScQueries) * 2 * kRowBytes + static_cast<size_t>(kScEntries) * 8 +
-                                static_cast<size_t>(kWinRowsCap + 1) * 4 + static_cast<size_t>(kScQueries) * 4;
+                                static_cast<size_t>(kWinRowsCap + 1) * 4 + static_cast<size_t>(kWinRowsCap) * 4 +
+                                static_cast<size_t>(kScQueries) * 4;
 
+__device__ __forceinline__ uint32_t hfma2_u32(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// The accumulation runs in the representation of the global accumulator itself: grad_out is staged as fp16 already
+// multiplied by the accumulator's power-of-two scale (f16_accum_scale: no sum of |weight * grad_out| over a whole image
+// can overflow), weights are fp16, a lane sums at most kScMaxRun products per register pair (HFMA2) and then issues one
+// packed fp16 reduction -- no unpack, scale or pack in the loop or in the flush.
 template <typename T>
 __global__ void __launch_bounds__(kScThreads, 3)
 msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
@@ -545,7 +707,8 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
   unsigned char* s_go = smem_raw;
   uint2* s_ent = reinterpret_cast<uint2*>(smem_raw + static_cast<size_t>(kScQueries) * 2 * kRowBytes);
   uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_ent + kScEntries);
-  int* s_qid = reinterpret_cast<int*>(s_cnt + kWinRowsCap + 1);
+  uint32_t* s_dst = s_cnt + kWinRowsCap + 1;
+  int* s_qid = reinterpret_cast<int*>(s_dst + kWinRowsCap);
   const uint32_t go_base = smem_u32(s_go);
 
   load_level_meta(meta, shapes, lsi, L);
@@ -559,97 +722,128 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
   const int grp = tid >> 2, c = tid & 3;                    // 4-lane group: one sorted range; lane = 8 channels
   const uint32_t go_lane = static_cast<uint32_t>(((grp & 1) * kRowBytes) + c * 16);   // copy of the row in "my" half of the banks
   const size_t pix_elems = static_cast<size_t>(M) * kD;
+  const int LP = L * P;
+  const float nanf_ = __int_as_float(0x7fc00000);
 
   for (long long work = blockIdx.x; work < total; work += gridDim.x) {
     const int head = static_cast<int>(work % M);
     const int tile = static_cast<int>((work / M) % tiles);
     const int b = static_cast<int>(work / (static_cast<long long>(M) * tiles));
     __syncthreads();
-    if (tid == 0) geom_tile(g, tile);
+    if (warp == 0) geom_tile(g, tile, lane);
     __syncthreads();
     const int nq = g.qoff[L];
-    __half* acc_img = gv16 + (static_cast<size_t>(b) * meta.accStride * M + head) * kD;
+    __half* acc_img = gv16 + (static_cast<size_t>(b) * meta.accStride * M + head) * kD + c * 8;
 
     for (int q0 = 0; q0 < nq; q0 += q_round) {
       const int nqr = min(q_round, nq - q0);
+      const int npts = nqr * P;
       __syncthreads();                      // previous round no longer reads go rows / query ids
-      // ---- stage the round's grad_out rows, twice: row q at both 64-byte halves of a 128-byte line, so that the two
-      //      4-lane groups of a quarter warp always read from disjoint banks ----
       for (int i = tid; i < nqr; i += kScThreads) s_qid[i] = tile_query(g, q0 + i, Lq);
       __syncthreads();
+      // ---- stage the round's grad_out rows as scaled fp16, twice: row q at both 64-byte halves of a 128-byte line, so
+      //      that the two 4-lane groups of a quarter warp always read from disjoint banks ----
       for (int i = tid; i < nqr * 4; i += kScThreads) {
         const int qi = i >> 2, ch = i & 3;
         const int q = s_qid[qi];
-        const size_t pair = (static_cast<size_t>(b) * Lq + (q >= 0 ? q : 0)) * M + head;
-        const uint4 u = q >= 0 ? ldg16(grad_out + pair * kD + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (q >= 0) {
+          const size_t pair = (static_cast<size_t>(b) * Lq + q) * M + head;
+          float f[8];
+          unpack16<T>(ldg16(grad_out + pair * kD + ch * 8), f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] *= gv_scale;
+          u = pack16<__half>(f);
+        }
         *reinterpret_cast<uint4*>(s_go + static_cast<size_t>(qi) * 2 * kRowBytes + ch * 16) = u;
         *reinterpret_cast<uint4*>(s_go + static_cast<size_t>(qi) * 2 * kRowBytes + kRowBytes + ch * 16) = u;
       }
+      // sampling locations / weights of one level's points: thread = point (slot tid + it * kScThreads)
+      float2 pxy[kScIters];
+      float pa[kScIters];
+      auto prefetch = [&](int l) {
+#pragma unroll
+        for (int it = 0; it < kScIters; ++it) {
+          const int idx = tid + it * kScThreads;
+          pxy[it] = make_float2(nanf_, nanf_);
+          pa[it] = 0.f;
+          if (idx < npts) {
+            const int qi = static_cast<int>(static_cast<uint32_t>(idx) / static_cast<uint32_t>(P)), p = idx - qi * P;
+            const int q = s_qid[qi];
+            if (q >= 0) {
+              const size_t pair = (static_cast<size_t>(b) * Lq + q) * M + head;
+              pxy[it] = __ldg(reinterpret_cast<const float2*>(loc) + pair * LP + l * P + p);
+              pa[it] = __ldg(attn + pair * LP + l * P + p);
+            }
+          }
+        }
+      };
+      prefetch(0);
 
       for (int l = 0; l < L; ++l) {
         const int H = g.H[l], W = g.W[l];
         const float Hf = static_cast<float>(H), Wf = static_cast<float>(W);
-        const int wdx = g.wdx[l], nrows = g.wdx[l] * g.wdy[l];
+        const int wdx = g.wdx[l], wdy = g.wdy[l], nrows = wdx * wdy;
         const int wx0 = g.wx0[l], wy0 = g.wy0[l];
         const int K = meta.accK[l];
         const size_t acc_row0 = static_cast<size_t>(meta.accBase[l]) + static_cast<size_t>(K > 1 ? tile % K : 0) * (static_cast<size_t>(H) * W);
         __syncthreads();                    // previous level's entries / counters are no longer read; go rows are staged
         for (int i = tid; i <= nrows; i += kScThreads) s_cnt[i] = 0u;
         __syncthreads();
-        // ---- count: thread = point; every valid corner inside the window takes a rank in its destination row's bin ----
+        // ---- count: every valid corner inside the window takes a rank in its destination row's bin ----
         uint32_t keyrank[kScIters][4];      // key | rank << 16; 0xFFFFFFFF = no entry
-        uint32_t payload[kScIters][4];      // local query << 16 | 16-bit weight
-        const int npts = nqr * P;
+        uint32_t payload[kScIters][4];      // fp16 weight, twice
 #pragma unroll
         for (int it = 0; it < kScIters; ++it) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) keyrank[it][k] = 0xFFFFFFFFu;
-          const int idx = tid + it * kScThreads;
-          if (idx < npts && s_qid[idx / P] >= 0) {
-            const int qi = idx / P, p = idx - qi * P;
-            const size_t pair = (static_cast<size_t>(b) * Lq + s_qid[qi]) * M + head;
-            const int lp = l * P + p;
-            const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + pair * (L * P) + lp);
-            const float a = __ldg(attn + pair * (L * P) + lp);
-            const PointGeo pg = point_geo(xy.x, xy.y, Hf, Wf);
-            if (pg.inside) {
-              const float ah = (1.f - pg.lh) * a, al = pg.lh * a;
-              const float hw = 1.f - pg.lw;
-              const float w[4] = {ah * hw, ah * pg.lw, al * hw, al * pg.lw};
+          const PointGeo pg = point_geo(pxy[it].x, pxy[it].y, Hf, Wf);
+          if (pg.inside) {
+            const float ah = (1.f - pg.lh) * pa[it], al = pg.lh * pa[it];
+            const float hw = 1.f - pg.lw;
+            const float w[4] = {ah * hw, ah * pg.lw, al * hw, al * pg.lw};
+            const int wxr0 = pg.ix - wx0, wyr0 = pg.iy - wy0;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int x = pg.ix + (k & 1), y = pg.iy + (k >> 1);
-                if (x < 0 || x >= W || y < 0 || y >= H || w[k] == 0.f) continue;   // zero padding / nothing to add
-                const int wxr = x - wx0, wyr = y - wy0;
-                if (wxr >= 0 && wxr < wdx && wyr >= 0 && wyr < g.wdy[l]) {
-                  const uint32_t key = static_cast<uint32_t>(wyr * wdx + wxr);
-                  const uint32_t rank = atomicAdd(&s_cnt[key], 1u);
-                  keyrank[it][k] = key | (rank << 16);
-                  payload[it][k] = (static_cast<uint32_t>(qi) << 16) | make_weight<T>(w[k]);
-                } else {
-                  // slow path: the whole 64-byte row of this corner, reduced straight into the accumulator
-                  const float ws = w[k] * gv_scale;
-                  __half* dst = acc_img + (acc_row0 + static_cast<size_t>(y) * W + x) * pix_elems;
+            for (int k = 0; k < 4; ++k) {
+              const int x = pg.ix + (k & 1), y = pg.iy + (k >> 1);
+              if (static_cast<unsigned>(x) >= static_cast<unsigned>(W) || static_cast<unsigned>(y) >= static_cast<unsigned>(H) || w[k] == 0.f)
+                continue;                                                        // zero padding / nothing to add
+              const int wxr = wxr0 + (k & 1), wyr = wyr0 + (k >> 1);
+              const __half2 w2 = __float2half2_rn(w[k]);
+              if (static_cast<unsigned>(wxr) < static_cast<unsigned>(wdx) && static_cast<unsigned>(wyr) < static_cast<unsigned>(wdy)) {
+                const uint32_t key = static_cast<uint32_t>(wyr * wdx + wxr);
+                const uint32_t rank = atomicAdd(&s_cnt[key], 1u);
+                keyrank[it][k] = key | (rank << 16);
+                payload[it][k] = *reinterpret_cast<const uint32_t*>(&w2);
+              } else {
+                // slow path: the whole 64-byte row of this corner, reduced straight into the accumulator
+                const int qi = static_cast<int>(static_cast<uint32_t>(tid + it * kScThreads) / static_cast<uint32_t>(P));
+                __half* dst = acc_img - c * 8 + (acc_row0 + static_cast<size_t>(y) * W + x) * pix_elems;
+                const uint32_t wbits = *reinterpret_cast<const uint32_t*>(&w2);
 #pragma unroll
-                  for (int ch = 0; ch < 4; ++ch) {
-                    float f[8];
-                    unpack16<T>(*reinterpret_cast<const uint4*>(s_go + static_cast<size_t>(qi) * 2 * kRowBytes + ch * 16), f);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] *= ws;
-                    red_add_16bit_x8<__half>(dst + ch * 8, pack16<__half>(f));
-                  }
+                for (int ch = 0; ch < 4; ++ch) {
+                  const uint4 u = *reinterpret_cast<const uint4*>(s_go + static_cast<size_t>(qi) * 2 * kRowBytes + ch * 16);
+                  uint4 r;
+                  r.x = hfma2_u32(wbits, u.x, 0u); r.y = hfma2_u32(wbits, u.y, 0u);
+                  r.z = hfma2_u32(wbits, u.z, 0u); r.w = hfma2_u32(wbits, u.w, 0u);
+                  red_add_16bit_x8<__half>(dst + ch * 8, r);
                 }
               }
             }
           }
         }
+        int qi_of[kScIters];
+#pragma unroll
+        for (int it = 0; it < kScIters; ++it)
+          qi_of[it] = static_cast<int>(static_cast<uint32_t>(tid + it * kScThreads) / static_cast<uint32_t>(P));
+        if (l + 1 < L) prefetch(l + 1);     // in flight during scan / place / sums
         __syncthreads();
-        // ---- exclusive scan of the bin counts (in place) ----
+        // ---- exclusive scan of the bin counts (in place) + destination pixel of every bin ----
         {
           const int per = (nrows + kScThreads - 1) / kScThreads;       // <= 6
-          const int r0 = tid * per;
+          const int r0 = tid * per, r1 = min(nrows, r0 + per);
           uint32_t sum = 0u;
-          for (int r = r0; r < min(nrows, r0 + per); ++r) sum += s_cnt[r];
+          for (int r = r0; r < r1; ++r) sum += s_cnt[r];
           uint32_t incl = sum;
 #pragma unroll
           for (int sft = 1; sft < 32; sft <<= 1) {
@@ -661,10 +855,15 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
           uint32_t woff = 0u;
           for (int w2 = 0; w2 < warp; ++w2) woff += s_warp_tot[w2];
           uint32_t run = woff + incl - sum;
-          for (int r = r0; r < min(nrows, r0 + per); ++r) {
-            const uint32_t cnt = s_cnt[r];
-            s_cnt[r] = run;
-            run += cnt;
+          if (r0 < r1) {
+            int wyr = static_cast<int>(static_cast<uint32_t>(r0) / static_cast<uint32_t>(wdx)), wxr = r0 - wyr * wdx;
+            for (int r = r0; r < r1; ++r) {
+              const uint32_t cnt = s_cnt[r];
+              s_cnt[r] = run;
+              run += cnt;
+              s_dst[r] = static_cast<uint32_t>((wy0 + wyr) * W + (wx0 + wxr));   // only read for bins that hold entries
+              if (++wxr == wdx) { wxr = 0; ++wyr; }
+            }
           }
           if (tid == kScThreads - 1) s_total = woff + incl;
         }
@@ -677,7 +876,7 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
             const uint32_t kr = keyrank[it][k];
             if (kr != 0xFFFFFFFFu) {
               const uint32_t key = kr & 0xFFFFu;
-              s_ent[s_cnt[key] + (kr >> 16)] = make_uint2(key, payload[it][k]);
+              s_ent[s_cnt[key] + (kr >> 16)] = make_uint2(key | (static_cast<uint32_t>(qi_of[it]) << 16), payload[it][k]);
             }
           }
         }
@@ -688,30 +887,24 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
           const int ngroups = kScThreads / 4;
           const int per = (E + ngroups - 1) / ngroups;
           const int e0 = grp * per, e1 = min(E, e0 + per);
-          float acc[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+          uint4 acc = make_uint4(0u, 0u, 0u, 0u);
           uint32_t cur = 0xFFFFFFFFu;
-          auto flush = [&](uint32_t key) {
-            const int wyr = static_cast<int>(key) / wdx, wxr = static_cast<int>(key) - wyr * wdx;
-            const size_t pix = static_cast<size_t>(wy0 + wyr) * W + (wx0 + wxr);
-            float f[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = acc[i] * gv_scale;
-            red_add_16bit_x8<__half>(acc_img + (acc_row0 + pix) * pix_elems + c * 8, pack16<__half>(f));
-          };
+          int e_flush = e0 + kScMaxRun;
+          __half* acc_lvl = acc_img + acc_row0 * pix_elems;
           for (int e = e0; e < e1; ++e) {
             const uint2 ent = s_ent[e];
-            if (ent.x != cur) {
-              if (cur != 0xFFFFFFFFu) flush(cur);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-              cur = ent.x;
+            const uint32_t key = ent.x & 0xFFFFu;
+            if (key != cur || e == e_flush) {
+              if (cur != 0xFFFFFFFFu) red_add_16bit_x8<__half>(acc_lvl + static_cast<size_t>(s_dst[cur]) * pix_elems, acc);
+              acc = make_uint4(0u, 0u, 0u, 0u);
+              cur = key;
+              e_flush = e + kScMaxRun;
             }
-            const uint4 u = lds128(go_base + (ent.y >> 16) * (2 * kRowBytes) + go_lane);
-            axpy16<T>(acc, u, ent.y & 0xFFFFu);
+            const uint4 u = lds128(go_base + (ent.x >> 16) * (2 * kRowBytes) + go_lane);
+            acc.x = hfma2_u32(ent.y, u.x, acc.x); acc.y = hfma2_u32(ent.y, u.y, acc.y);
+            acc.z = hfma2_u32(ent.y, u.z, acc.z); acc.w = hfma2_u32(ent.y, u.w, acc.w);
           }
-          if (cur != 0xFFFFFFFFu) flush(cur);
+          if (cur != 0xFFFFFFFFu) red_add_16bit_x8<__half>(acc_lvl + static_cast<size_t>(s_dst[cur]) * pix_elems, acc);
         }
       }
     }
