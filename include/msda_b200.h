@@ -73,7 +73,16 @@ enum {
    * added, unscaled, with packed 16-bit reductions in the value dtype straight into the zeroed grad_value rows, so the
    * dense zero / sum / round passes over the accumulator (most of a decoder layer's backward) are paid for the coarse
    * levels only.  This flag switches that off (every level goes through the fp16 buckets). */
-  MSDA_BWD_NO_SPARSE_DIRECT = 4
+  MSDA_BWD_NO_SPARSE_DIRECT = 4,
+  /* Default mode, cluster guard.  Both 16-bit mechanisms above size their precision for evenly spread sampling.  For
+   * calls of at most 4 Mi sampling points (decoder cross-attention; the dense encoder shapes are far larger and spread
+   * by construction) msda_backward first counts the sampling points per (run of 4 pixels, head) on the device; if a cell
+   * holds more than its level tolerates (32 for a sparse level, 512 per bucket otherwise -- e.g. every query looking at
+   * the same object) it raises a flag in the control block of `scratch`.  The 16-bit pipeline and an fp32-accumulation
+   * pipeline are both enqueued, and every kernel returns at once unless the flag selects its pipeline: no host
+   * synchronisation, same results as MSDA_BWD_GRAD_VALUE_FP32_ACCUM when the flag is up.  Not applied to the fused
+   * pre-op entry points (they never see sampling locations).  This flag switches the guard off. */
+  MSDA_BWD_NO_CLUSTER_GUARD = 8
 };
 #define MSDA_BWD_ACCUM_DEPTH(depth) (((depth) & 0xffff) << 8)
 
@@ -122,8 +131,7 @@ int msda_backward(const void* value, const int64_t* spatial_shapes, const int64_
  * These entry points read such a view in place and write `grad_value` into the matching view of one shared
  * (N, S, layers, M*D) gradient buffer, so the stacked projection needs no per-layer copies in either direction.
  * Strides are in elements, >= M*D, multiples of 16 bytes; 0 means dense.  Pointers address element [0, 0, 0, 0] of
- * the view.  Vector kernels only (head dim 16/32/64/128, not float64), 16-bit values in the default accumulation
- * mode; otherwise MSDA_ERR_BAD_STRIDE.  `msda_forward` / `msda_backward` are these with both strides 0.
+ * the view.  Vector kernels only (head dim 16/32/64/128, not float64); otherwise MSDA_ERR_BAD_STRIDE.  `msda_forward` / `msda_backward` are these with both strides 0.
  */
 int msda_forward_strided(const void* value, long long value_pixel_stride,
                          const int64_t* spatial_shapes, const int64_t* level_start_index,

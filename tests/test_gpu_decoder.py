@@ -13,6 +13,7 @@ from tests.test_gpu_parity import TOL, _with_flags, check, ops, oracle_on_rounde
 pytestmark = pytest.mark.gpu
 
 NO_SPARSE = 4        # MSDA_BWD_NO_SPARSE_DIRECT
+NO_GUARD = 8         # MSDA_BWD_NO_CLUSTER_GUARD
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -37,6 +38,75 @@ def test_sparse_levels_add_directly_into_grad_value(ops, dtype, shapes, Lq):
     e_fast, e_bucketed = rel_to_max(fast[1], want), rel_to_max(bucketed[1], want)
     assert e_fast < TOL[dtype] and e_bucketed < TOL[dtype]
     assert e_fast < 2.5 * max(e_bucketed, 2e-3), (e_fast, e_bucketed)
+
+
+def _clustered_decoder_problem(spread, mean, N=2, Lq=300, seed=7):
+    """cfg4 geometry; every query box is drawn inside a square of side `spread` (fraction of the image)."""
+    from vision_instance_seg_b200 import workloads as W
+    cfg = W.CONFIGS["cfg4_decoder_300q_bf16"]
+    ss = W.make_spatial_shapes(cfg["shapes"])
+    S, L, M, D, P = int(ss.prod(1).sum()), 4, 8, 32, 4
+    g = torch.Generator().manual_seed(seed)
+    value = torch.randn(N, S, M, D, generator=g)
+    ctr = 0.5 + (torch.rand(N, Lq, 1, 2, generator=g) - 0.5) * spread
+    wh = (torch.rand(N, Lq, 1, 2, generator=g) * 0.4 + 0.1) * spread
+    off = W.init_offset_pattern(M, L, P)[None, None] + torch.randn(N, Lq, M, L, P, 2, generator=g)
+    loc = (ctr[:, :, None, :, None, :] + off / P * wh[:, :, None, :, None, :] * 0.5).contiguous()
+    attn = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P)
+    go = torch.randn(N, Lq, M * D, generator=g) + mean
+    return value, ss, lsi_of(ss), loc, attn, go
+
+
+@pytest.mark.parametrize("mean", [0.0, 1.0])
+@pytest.mark.parametrize("spread", [1.0, 0.3, 0.1, 0.03, 0.01])
+def test_default_backward_holds_the_gate_when_queries_cluster(ops, spread, mean):
+    """Round-1 finding (profiles/sparse_accuracy_r01.jsonl): with every query looking at 3 % of the image both 16-bit
+    accumulation modes drift past 2e-2 on grad_value.  The cluster guard (include/msda_b200.h) counts sampling points
+    per (4-pixel run, head) on the device and switches such a call to fp32 accumulation; the DEFAULT flags must hold the
+    bf16 gate over the whole range, from evenly spread boxes down to all 300 queries on ~1 % of the image."""
+    problem = _clustered_decoder_problem(spread, mean)
+    check(ops, problem, torch.bfloat16)
+
+
+def _cluster_flag_after_backward(problem, flags=0):
+    """Raw C ABI call with a caller-owned scratch, then the guard's flag word (ctrl[1]) read back from it."""
+    from vision_instance_seg_b200 import _lib
+    lib = _lib.load_library()
+    dev = "cuda:0"
+    value, ss, lsi, loc, attn, go = problem
+    v = value.to(dev, torch.bfloat16).contiguous()
+    lo, at = loc.to(dev, torch.float32).contiguous(), attn.to(dev, torch.float32).contiguous()
+    g = go.to(dev, torch.bfloat16).contiguous()
+    ssd, lsid = ss.to(dev), lsi.to(dev)
+    N, S, M, D = v.shape
+    Lq, L, P = lo.shape[1], lo.shape[3], lo.shape[4]
+    nbytes = lib.msda_backward_scratch_bytes(N, S, M, D, Lq, L, P, _lib.MSDA_BF16, flags)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    gv, gl, ga = torch.empty_like(v), torch.empty_like(lo), torch.empty_like(at)
+    rc = lib.msda_backward(v.data_ptr(), ssd.data_ptr(), lsid.data_ptr(), lo.data_ptr(), at.data_ptr(), g.data_ptr(),
+                           gv.data_ptr(), gl.data_ptr(), ga.data_ptr(), scratch.data_ptr(), nbytes,
+                           N, S, M, D, Lq, L, P, _lib.MSDA_BF16, 64, flags, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    return int(scratch[:8].view(torch.int32)[1]), gv
+
+
+def test_cluster_guard_raises_its_flag_only_when_queries_cluster(ops):
+    """Evenly spread and mildly clustered boxes keep the 16-bit pipeline (flag 0); all queries on a few per cent of the
+    image switch the call to fp32 accumulation (flag 1), which is then as accurate as asking for it explicitly."""
+    for spread, want_flag in ((1.0, 0), (0.3, 0), (0.03, 1), (0.01, 1)):
+        flag, _ = _cluster_flag_after_backward(_clustered_decoder_problem(spread, 0.0))
+        assert flag == want_flag, (spread, flag)
+    problem = _clustered_decoder_problem(0.02, 1.0)
+    value, ss, lsi, loc, attn, go = problem
+    want = oracle_on_rounded_inputs(value, ss, loc, attn, go, torch.bfloat16)[1]
+    flag, gv_guarded = _cluster_flag_after_backward(problem)
+    _, gv_fp32 = _cluster_flag_after_backward(problem, flags=2)
+    flag_off, gv_unguarded = _cluster_flag_after_backward(problem, flags=NO_GUARD)
+    assert flag == 1 and flag_off == 0
+    e_guarded, e_fp32, e_unguarded = rel_to_max(gv_guarded, want), rel_to_max(gv_fp32, want), rel_to_max(gv_unguarded, want)
+    assert e_guarded < 5e-3 and abs(e_guarded - e_fp32) < 1e-3, (e_guarded, e_fp32)
+    assert e_unguarded > 2 * e_guarded, (e_unguarded, e_guarded)       # what the guard is for
 
 
 @pytest.mark.parametrize("D", [16, 64, 128])

@@ -59,9 +59,18 @@ def test_argument_validation_without_gpu(built_library):
     # ... bucketed fp16 accumulation (default) = 256-byte control block + N * rows_bound * M * D halves,
     # rows_bound = L * (ceil(Lq*P/depth) + 1) + 2*S
     rows = 2 * ((7 * 4 + 31) // 32 + 1) + 2 * 10
-    assert lib.msda_backward_scratch_bytes(2, 10, 8, 32, 7, 2, 4, _lib.MSDA_BF16, 0) == 256 + 2 * rows * 8 * 32 * 2
+    ng = _lib.MSDA_BWD_NO_CLUSTER_GUARD
+    assert lib.msda_backward_scratch_bytes(2, 10, 8, 32, 7, 2, 4, _lib.MSDA_BF16, ng) == 256 + 2 * rows * 8 * 32 * 2
     rows4 = 2 * ((7 * 4 + 3) // 4 + 1) + 2 * 10
-    assert lib.msda_backward_scratch_bytes(2, 10, 8, 32, 7, 2, 4, _lib.MSDA_F16, _lib.accum_depth_flag(4)) == 256 + 2 * rows4 * 8 * 32 * 2
+    assert lib.msda_backward_scratch_bytes(2, 10, 8, 32, 7, 2, 4, _lib.MSDA_F16, _lib.accum_depth_flag(4) | ng) == 256 + 2 * rows4 * 8 * 32 * 2
+    # ... with the cluster guard (default for calls of <= 4 Mi sampling points): + per-(4-pixel run, head) counters,
+    # rounded up to 256 bytes, and a payload large enough for either accumulation mode
+    counters = -(-(2 * ((10 + 3) // 4 + 1) * 8 * 4) // 256) * 256
+    assert lib.msda_backward_scratch_bytes(2, 10, 8, 32, 7, 2, 4, _lib.MSDA_BF16, 0) == \
+        256 + counters + max(2 * rows * 8 * 32 * 2, 2 * 10 * 8 * 32 * 4)
+    # a call too large for the density pass is sized as without the guard
+    big = (16, 21760, 8, 32, 21760, 4, 4)
+    assert lib.msda_backward_scratch_bytes(*big, _lib.MSDA_BF16, 0) == lib.msda_backward_scratch_bytes(*big, _lib.MSDA_BF16, ng)
     assert lib.msda_backward_scratch_bytes(2, 10, 8, 30, 7, 2, 4, _lib.MSDA_BF16, 0) == 2 * 10 * 8 * 30 * 4   # compat kernels
     assert lib.msda_backward_scratch_bytes(2, 10, 8, 32, 7, 2, 4, _lib.MSDA_F32, 0) == 0
 

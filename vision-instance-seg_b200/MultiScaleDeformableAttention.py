@@ -27,7 +27,8 @@ _DTYPES = {torch.float32: _lib.MSDA_F32, torch.float64: _lib.MSDA_F64,
 #: 16-bit values, MSDA_B200_ACCUM_DEPTH=<n> overrides the fp16 bucket depth
 backward_flags = (_lib.MSDA_BWD_GRAD_VALUE_FP32_ACCUM if os.environ.get("MSDA_B200_FP32_ACCUM") == "1"
                   else _lib.MSDA_BWD_DEFAULT) | _lib.accum_depth_flag(int(os.environ.get("MSDA_B200_ACCUM_DEPTH", "0"))) \
-    | (_lib.MSDA_BWD_NO_SPARSE_DIRECT if os.environ.get("MSDA_B200_NO_SPARSE_DIRECT") == "1" else 0)
+    | (_lib.MSDA_BWD_NO_SPARSE_DIRECT if os.environ.get("MSDA_B200_NO_SPARSE_DIRECT") == "1" else 0) \
+    | (_lib.MSDA_BWD_NO_CLUSTER_GUARD if os.environ.get("MSDA_B200_NO_CLUSTER_GUARD") == "1" else 0)
 
 
 def _require(t: torch.Tensor, name: str) -> None:

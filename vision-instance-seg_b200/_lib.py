@@ -19,6 +19,7 @@ MSDA_F32, MSDA_F64, MSDA_BF16, MSDA_F16 = 0, 1, 2, 3
 MSDA_BWD_DEFAULT = 0
 MSDA_BWD_GRAD_VALUE_FP32_ACCUM = 2
 MSDA_BWD_NO_SPARSE_DIRECT = 4
+MSDA_BWD_NO_CLUSTER_GUARD = 8
 
 
 def accum_depth_flag(depth: int) -> int:

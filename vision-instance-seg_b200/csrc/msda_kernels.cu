@@ -342,6 +342,12 @@ msda_fwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
 // =====================================================================================================
 // Backward, vector path
 // =====================================================================================================
+// Cluster guard (see msda_cluster_density_kernel): the launcher enqueues the 16-bit and the fp32 accumulation pipeline
+// back to back; every kernel of a pipeline returns at once unless the flag in the control block selects it.
+__device__ __forceinline__ bool gated_off(const uint32_t* __restrict__ gate, int want) {
+  return gate != nullptr && ((__ldg(gate) != 0u) != (want != 0));
+}
+
 // Reduce-scatter of per-lane partial sums inside a G-lane group: every lane enters with R values for each of
 // G consecutive sampling points and leaves with the group totals of the point whose index equals its lane
 // position c.  (R*(G-1) shuffles per G points instead of R*log2(G) per point.)
@@ -395,7 +401,9 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
                     float* __restrict__ gv32, __half* __restrict__ gv16, T* __restrict__ gv_direct,
                     const uint32_t* __restrict__ ctrl,
                     AT* __restrict__ grad_loc, AT* __restrict__ grad_attn,
-                    int S, int M, int Lq, int L, int P, int total_pairs, int depth, int vps, int gps) {
+                    int S, int M, int Lq, int L, int P, int total_pairs, int depth, int vps, int gps,
+                    const uint32_t* __restrict__ gate, int gate_want) {
+  if (gated_off(gate, gate_want)) return;   // cluster guard: the other accumulation mode handles this call
   // vps: elements between neighbouring pixels of `value`; gps: the same for the buffer laid out like value that receives
   // reductions directly (gv32, or gv_direct for the sparse levels of GV16 mode: see build_accum_layout)
   constexpr int VEC = 16 / sizeof(T);
@@ -611,23 +619,45 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   }
 }
 
-// fp32 accumulation buffer -> 16-bit grad_value (one rounding per element)
+// fp32 accumulation buffer (dense, laid out like value) -> 16-bit grad_value (one rounding per element); gps = elements
+// between neighbouring pixels of dst, vpp = 16-byte output vectors per pixel row
 template <typename T>
 __global__ void __launch_bounds__(256)
-msda_round_scratch_kernel(const float* __restrict__ src, T* __restrict__ dst, size_t n8) {
+msda_round_scratch_kernel(const float* __restrict__ src, T* __restrict__ dst, size_t n8, uint32_t vpp, uint32_t gps,
+                          const uint32_t* __restrict__ gate, int gate_want) {
+  if (gated_off(gate, gate_want)) return;
+  const bool dense = gps == vpp * 8u;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const float4 a = __ldcs(reinterpret_cast<const float4*>(src) + 2 * i);
     const float4 b = __ldcs(reinterpret_cast<const float4*>(src) + 2 * i + 1);
     const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    reinterpret_cast<uint4*>(dst)[i] = pack16<T>(f);
+    if (dense) {
+      reinterpret_cast<uint4*>(dst)[i] = pack16<T>(f);
+    } else {
+      const size_t pix = i / vpp;
+      const uint32_t v = static_cast<uint32_t>(i - pix * vpp);
+      *reinterpret_cast<uint4*>(dst + pix * gps + v * 8u) = pack16<T>(f);
+    }
   }
+}
+
+// gated memset (the fp32 accumulation buffer of the cluster guard's second pipeline)
+static __global__ void __launch_bounds__(256)
+msda_zero_fill_kernel(uint4* __restrict__ p, size_t n16, const uint32_t* __restrict__ gate, int gate_want) {
+  if (gated_off(gate, gate_want)) return;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    p[i] = z;
 }
 
 // max |x| over a 16-bit tensor -> ctrl[0] (bits of a non-negative float order like unsigned integers)
 template <typename T>
 __global__ void __launch_bounds__(256)
-msda_absmax_kernel(const T* __restrict__ x, size_t n8, uint32_t* __restrict__ ctrl) {
+msda_absmax_kernel(const T* __restrict__ x, size_t n8, uint32_t* __restrict__ ctrl, const uint32_t* __restrict__ gate,
+                   int gate_want) {
+  if (gated_off(gate, gate_want)) return;
   float m = 0.f;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -648,7 +678,8 @@ msda_absmax_kernel(const T* __restrict__ x, size_t n8, uint32_t* __restrict__ ct
 static __global__ void __launch_bounds__(256)
 msda_zero_f16_buckets_kernel(uint4* __restrict__ scratch, size_t ctrl_vecs, const int64_t* __restrict__ shapes,
                              const int64_t* __restrict__ lsi, uint16_t* __restrict__ gv, int N, int S, int M, int D,
-                             int Lq, int L, int P, int depth, int gps) {
+                             int Lq, int L, int P, int depth, int gps, const uint32_t* __restrict__ gate, int gate_want) {
+  if (gated_off(gate, gate_want)) return;
   __shared__ LevelMeta meta;
   load_level_meta(meta, shapes, lsi, L);
   build_accum_layout(meta, L, Lq, P, depth, gv != nullptr);
@@ -678,7 +709,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 msda_round_f16_buckets_kernel(const __half* __restrict__ acc, T* __restrict__ dst, const int64_t* __restrict__ shapes,
                               const int64_t* __restrict__ lsi, const uint32_t* __restrict__ ctrl,
-                              int N, int S, int M, int D, int Lq, int L, int P, int depth, int sparse_direct, int gps) {
+                              int N, int S, int M, int D, int Lq, int L, int P, int depth, int sparse_direct, int gps,
+                              const uint32_t* __restrict__ gate, int gate_want) {
+  if (gated_off(gate, gate_want)) return;
   __shared__ LevelMeta meta;
   load_level_meta(meta, shapes, lsi, L);
   build_accum_layout(meta, L, Lq, P, depth, sparse_direct != 0);
@@ -711,6 +744,44 @@ msda_round_f16_buckets_kernel(const __half* __restrict__ acc, T* __restrict__ ds
     for (int j = 0; j < 8; ++j) sum[j] *= inv;
     *reinterpret_cast<uint4*>(dst + pix * gps + v * 8) = pack16<T>(sum);
   }
+}
+
+// =====================================================================================================
+// Cluster guard.  The 16-bit accumulation modes size their precision for evenly spread sampling: an fp16 bucket is
+// meant to receive ~depth adds, a sparse level's grad_value element zero or one.  When many queries crowd onto a few
+// pixels (measured: > 1 000 sampling points on one pixel of the 300-query decoder shape) both drift past the 2e-2 gate,
+// while fp32 accumulation does not care.  For calls small enough that one more pass over sampling_loc is noise
+// (kGuardMaxPoints), this kernel counts the sampling points per (run of 4 pixels, head) -- top-left corner, all four
+// corners land within one pixel of it -- and raises ctrl[1] as soon as a cell holds more than its level tolerates:
+// 32 points for a sparse level (packed adds in the value dtype), 512 per bucket for a bucketed one (fp16, ~11 bits).  Every kernel of the
+// two accumulation pipelines then checks the flag (gated_off) and only the selected pipeline does any work.
+// =====================================================================================================
+constexpr int kGuardSparseLimit = 32;
+constexpr int kGuardBucketLimit = 512;
+
+static __global__ void __launch_bounds__(256)
+msda_cluster_density_kernel(const float* __restrict__ loc, const int64_t* __restrict__ shapes,
+                            const int64_t* __restrict__ lsi, uint32_t* __restrict__ counters, uint32_t* __restrict__ ctrl,
+                            long long total_points, int cells, int M, int Lq, int L, int P, int depth, int sparse_direct) {
+  __shared__ LevelMeta meta;
+  load_level_meta(meta, shapes, lsi, L);
+  build_accum_layout(meta, L, Lq, P, depth, sparse_direct != 0);
+  bool over = false;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total_points;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int l = static_cast<int>((idx / P) % L);
+    const int m = static_cast<int>((idx / (static_cast<long long>(P) * L)) % M);
+    const long long b = idx / (static_cast<long long>(P) * L * M * Lq);
+    const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + idx);
+    const int H = meta.H[l], W = meta.W[l];
+    const Taps t = make_taps(xy.x, xy.y, H, W, static_cast<float>(H), static_cast<float>(W));
+    if (!t.inside) continue;
+    const uint32_t cell = static_cast<uint32_t>(meta.start[l] + t.i00) >> 2;
+    const uint32_t c = atomicAdd(counters + (static_cast<size_t>(b) * cells + cell) * M + m, 1u) + 1u;
+    const int K = meta.accK[l];
+    over |= c > static_cast<uint32_t>(K == 0 ? kGuardSparseLimit : kGuardBucketLimit * K);
+  }
+  if (__any_sync(0xffffffffu, over) && (threadIdx.x & 31) == 0) atomicOr(ctrl + 1, 1u);
 }
 
 // Tiled kernels for the dense encoder call site (Lq == S): shared-memory value windows, sorted grad_value sums
@@ -873,6 +944,17 @@ std::atomic<long long> g_total_launches{0};
 std::atomic<int> g_tiled_mode{-1};         // msda_set_tiled_mode(); -1 = take MSDA_B200_TILED (default 0) from the environment on first use
 #endif
 
+// SM count of the current device (cached per thread; one process drives one GPU)
+static int device_sm_count() {
+  static thread_local int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
+      sms = 148;
+  }
+  return sms;
+}
+
 static bool tiled_enabled() {
   int m = g_tiled_mode.load(std::memory_order_relaxed);
   if (m < 0) {
@@ -918,6 +1000,9 @@ struct Problem {
   int R = 0;
   bool aux16 = false;           // fused pre-op only: offsets / logits (and their gradients) are in the 16-bit value type
   long long vps = 0, gps = 0;   // elements between neighbouring pixels of value / grad_value (0 = dense, M*D)
+  // cluster guard: when set, a backward kernel returns at once unless (*gate != 0) == (gate_want != 0)
+  const uint32_t* gate = nullptr;
+  int gate_want = 0;
   int value_stride() const { return static_cast<int>(vps > 0 ? vps : static_cast<long long>(M) * D); }
   int grad_stride() const { return static_cast<int>(gps > 0 ? gps : static_cast<long long>(M) * D); }
   bool strided() const { return value_stride() != M * D || grad_stride() != M * D; }
@@ -1127,7 +1212,8 @@ static int launch_bwd_vec_impl(const Problem& pr, const void* value, const int64
         kernel<<<grid, kThreads, smem, st>>>(
             static_cast<const T*>(value), shapes, lsi, static_cast<const AT*>(loc), static_cast<const AT*>(attn),
             pr.ref, pr.R, static_cast<const T*>(go), nullptr, gv16, static_cast<T*>(gv_direct), ctrl, static_cast<AT*>(gloc),
-            static_cast<AT*>(gattn), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth, pr.value_stride(), gv_stride);
+            static_cast<AT*>(gattn), pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth, pr.value_stride(), gv_stride,
+            pr.gate, pr.gate_want);
         ++g_last_launches, ++g_total_launches;
         return static_cast<int>(cudaGetLastError());
       };
@@ -1141,7 +1227,7 @@ static int launch_bwd_vec_impl(const Problem& pr, const void* value, const int64
   msda_bwd_vec_kernel<T, D, false, FUSED, AT, false><<<grid, kThreads, smem, st>>>(
       static_cast<const T*>(value), shapes, lsi, static_cast<const AT*>(loc), static_cast<const AT*>(attn),
       pr.ref, pr.R, static_cast<const T*>(go), gv32, nullptr, nullptr, nullptr, static_cast<AT*>(gloc), static_cast<AT*>(gattn),
-      pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth, pr.value_stride(), gv_stride);
+      pr.S, pr.M, pr.Lq, pr.L, pr.P, pr.total_pairs, depth, pr.value_stride(), gv_stride, pr.gate, pr.gate_want);
   ++g_last_launches, ++g_total_launches;
   return static_cast<int>(cudaGetLastError());
 }
@@ -1160,121 +1246,218 @@ static int launch_bwd_vec(const Problem& pr, const void* value, const int64_t* s
   return launch_bwd_vec_impl<T, D, false, float>(pr, value, shapes, lsi, loc, attn, go, gv32, gv16, gvd, gvs, ctrl, gloc, gattn, use16, depth, st);
 }
 
+// ---- scratch layout of the 16-bit backward ---------------------------------------------------------------
+//   [ control block kF16CtrlBytes ][ cluster-guard counters ][ payload ]
+// control block: ctrl[0] = bits of max|grad_out|, ctrl[1] = cluster flag.  The counters exist only for calls the guard
+// covers (by size alone, so that msda_backward_scratch_bytes and the launcher always agree); the payload is the scaled
+// fp16 bucket accumulator or, when the guard may switch to it, the larger of that and a dense fp32 copy of grad_value.
+constexpr long long kGuardMaxPoints = 4ll << 20;     // sampling points per call up to which the density pass runs
+
+struct ScratchLayout {
+  bool guard;
+  int cells;                 // 4-pixel cells per image (+1)
+  size_t counters_off, counters_bytes, payload_off, total;
+};
+
+static ScratchLayout scratch_layout_16(int N, int S, int M, int D, int Lq, int L, int P, int flags) {
+  ScratchLayout sl{};
+  const long long points = static_cast<long long>(N) * Lq * M * L * P;
+  sl.guard = !(flags & MSDA_BWD_NO_CLUSTER_GUARD) && points <= kGuardMaxPoints;
+  sl.cells = (S + 3) / 4 + 1;
+  sl.counters_off = kF16CtrlBytes;
+  sl.counters_bytes = sl.guard ? ((static_cast<size_t>(N) * sl.cells * M * sizeof(uint32_t) + 255) & ~static_cast<size_t>(255)) : 0;
+  sl.payload_off = sl.counters_off + sl.counters_bytes;
+  size_t payload = f16_scratch_bytes(N, S, M, D, Lq, L, P, accum_depth(flags)) - kF16CtrlBytes;
+  if (sl.guard) payload = std::max(payload, static_cast<size_t>(N) * S * M * D * sizeof(float));
+  sl.total = sl.payload_off + payload;
+  return sl;
+}
+
+// 16-bit values, fp32 accumulation: zero the dense fp32 buffer, backward kernel with red.v4.f32, one rounding pass.
+// `gated`: part of the cluster guard's pair of pipelines (kernels check pr.gate; the memset becomes a gated kernel).
 template <typename T>
-MSDA_LAUNCHER int launch_bwd(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
+static int run_bwd_fp32_accum(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
+                              const void* loc, const void* attn, const void* go, void* gv, void* gloc, void* gattn,
+                              float* acc32, int depth, bool gated, cudaStream_t st) {
+  const size_t n_value = static_cast<size_t>(pr.N) * pr.S * pr.M * pr.D;
+  const int sms = device_sm_count();
+  cudaError_t e;
+  if (gated) {
+    const size_t n16 = n_value * sizeof(float) / 16;
+    msda_zero_fill_kernel<<<static_cast<int>(std::min<size_t>((n16 + 255) / 256, static_cast<size_t>(sms) * 8)), 256, 0, st>>>(
+        reinterpret_cast<uint4*>(acc32), n16, pr.gate, pr.gate_want);
+    ++g_last_launches, ++g_total_launches;
+    e = cudaGetLastError();
+  } else {
+    e = cudaMemsetAsync(acc32, 0, n_value * sizeof(float), st);
+  }
+  if (e != cudaSuccess) return static_cast<int>(e);
+  int rc;
+  if (vec_supported<T>(pr)) {
+    const int gvs = pr.M * pr.D;                         // the fp32 buffer is dense
+    switch (pr.D) {
+      case 16: rc = launch_bwd_vec<T, 16>(pr, value, shapes, lsi, loc, attn, go, acc32, nullptr, nullptr, gvs, nullptr, gloc, gattn, false, depth, st); break;
+      case 32: rc = launch_bwd_vec<T, 32>(pr, value, shapes, lsi, loc, attn, go, acc32, nullptr, nullptr, gvs, nullptr, gloc, gattn, false, depth, st); break;
+      case 64: rc = launch_bwd_vec<T, 64>(pr, value, shapes, lsi, loc, attn, go, acc32, nullptr, nullptr, gvs, nullptr, gloc, gattn, false, depth, st); break;
+      default: rc = launch_bwd_vec<T, 128>(pr, value, shapes, lsi, loc, attn, go, acc32, nullptr, nullptr, gvs, nullptr, gloc, gattn, false, depth, st); break;
+    }
+  } else {
+    if (pr.ref) return MSDA_ERR_FUSED_UNSUPPORTED;
+    using Aux = typename Traits<T>::Aux;
+    const int grid = (pr.total_pairs + kWarps - 1) / kWarps;
+    msda_bwd_any_kernel<T, float><<<grid, kThreads, 0, st>>>(
+        static_cast<const T*>(value), shapes, lsi, static_cast<const Aux*>(loc), static_cast<const Aux*>(attn),
+        static_cast<const T*>(go), acc32, static_cast<Aux*>(gloc), static_cast<Aux*>(gattn),
+        pr.S, pr.M, pr.D, pr.Lq, pr.L, pr.P, pr.total_pairs);
+    ++g_last_launches, ++g_total_launches;
+    rc = static_cast<int>(cudaGetLastError());
+  }
+  if (rc != 0) return rc;
+  if ((n_value & 7) == 0 && (pr.M * pr.D) % 8 == 0) {
+    const size_t n8 = n_value / 8;
+    const int grid = static_cast<int>(std::min<size_t>((n8 + 255) / 256, static_cast<size_t>(sms) * 16));
+    msda_round_scratch_kernel<T><<<grid, 256, 0, st>>>(acc32, static_cast<T*>(gv), n8, static_cast<uint32_t>(pr.M * pr.D / 8),
+                                                      static_cast<uint32_t>(pr.grad_stride()), pr.gate, pr.gate_want);
+  } else {
+    const int grid = static_cast<int>(std::min<size_t>((n_value + 255) / 256, static_cast<size_t>(sms) * 16));
+    msda_round_scratch_any_kernel<T><<<grid, 256, 0, st>>>(acc32, static_cast<T*>(gv), n_value);
+  }
+  ++g_last_launches, ++g_total_launches;
+  return static_cast<int>(cudaGetLastError());
+}
+
+// 16-bit values, scaled fp16 buckets (+ sparse levels added directly): zero, max|grad_out|, backward, sum + round.
+template <typename T>
+static int run_bwd_f16_accum(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
+                             const void* loc, const void* attn, const void* go, void* gv, void* gloc, void* gattn,
+                             uint32_t* ctrl, __half* acc16, bool zero_ctrl, int flags, cudaStream_t st) {
+  const int sms = device_sm_count();
+  const int gstride = pr.grad_stride();
+  // tiled kernels: one reduction per (destination row, tile) reaches the accumulator -- at most a few hundred adds per
+  // element on the coarsest level of a pyramid -- so a single copy per level (no buckets) keeps the fp16 error at ~2e-3
+  const bool tiled = tiled_supported<T>(pr) && pr.gate == nullptr;
+  const int depth = tiled ? 0xffff : accum_depth(flags);
+  // a level can only be sparse (4*Lq*P <= H_l*W_l) if 4*Lq*P <= S: decided here, the levels themselves on the device
+  const bool sparse_direct = !(flags & MSDA_BWD_NO_SPARSE_DIRECT) && kSparseFactor * pr.Lq * pr.P <= pr.S;
+  // the control block sits right in front of the accumulator only without the guard's counters in between
+  uint4* zero_base = zero_ctrl ? reinterpret_cast<uint4*>(ctrl) : reinterpret_cast<uint4*>(acc16);
+  msda_zero_f16_buckets_kernel<<<sms * 8, 256, 0, st>>>(zero_base, zero_ctrl ? kF16CtrlBytes / 16 : 0, shapes, lsi,
+                                                       sparse_direct ? static_cast<uint16_t*>(gv) : nullptr,
+                                                       pr.N, pr.S, pr.M, pr.D, pr.Lq, pr.L, pr.P, depth, gstride,
+                                                       pr.gate, pr.gate_want);
+  ++g_last_launches, ++g_total_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return static_cast<int>(e);
+  int rc;
+  if (tiled) {
+    rc = launch_bwd_tiled<T>(pr, value, shapes, lsi, loc, attn, go, acc16, ctrl, gloc, gattn, depth, st);
+  } else {
+    const size_t n8 = static_cast<size_t>(pr.N) * pr.Lq * pr.M * pr.D / 8;     // D is a multiple of 16 here
+    const int grid = static_cast<int>(std::min<size_t>((n8 + 255) / 256, static_cast<size_t>(sms) * 8));
+    msda_absmax_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(go), n8, ctrl, pr.gate, pr.gate_want);
+    ++g_last_launches, ++g_total_launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+    void* gvd = sparse_direct ? gv : nullptr;                      // sparse levels add straight into grad_value
+    switch (pr.D) {
+      case 16: rc = launch_bwd_vec<T, 16>(pr, value, shapes, lsi, loc, attn, go, nullptr, acc16, gvd, gstride, ctrl, gloc, gattn, true, depth, st); break;
+      case 32: rc = launch_bwd_vec<T, 32>(pr, value, shapes, lsi, loc, attn, go, nullptr, acc16, gvd, gstride, ctrl, gloc, gattn, true, depth, st); break;
+      case 64: rc = launch_bwd_vec<T, 64>(pr, value, shapes, lsi, loc, attn, go, nullptr, acc16, gvd, gstride, ctrl, gloc, gattn, true, depth, st); break;
+      default: rc = launch_bwd_vec<T, 128>(pr, value, shapes, lsi, loc, attn, go, nullptr, acc16, gvd, gstride, ctrl, gloc, gattn, true, depth, st); break;
+    }
+  }
+  if (rc != 0) return rc;
+  const size_t n8_img = static_cast<size_t>(pr.S) * pr.M * pr.D / 8;
+  const size_t want = (n8_img + 255) / 256, cap = std::max<size_t>(1, (static_cast<size_t>(sms) * 16) / static_cast<size_t>(pr.N));
+  const dim3 grid(static_cast<unsigned>(std::min(want, cap)), static_cast<unsigned>(std::min(pr.N, 65535)));
+  msda_round_f16_buckets_kernel<T><<<grid, 256, 0, st>>>(acc16, static_cast<T*>(gv), shapes, lsi, ctrl, pr.N, pr.S,
+                                                        pr.M, pr.D, pr.Lq, pr.L, pr.P, depth, sparse_direct && !tiled ? 1 : 0,
+                                                        gstride, pr.gate, pr.gate_want);
+  ++g_last_launches, ++g_total_launches;
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <typename T>
+MSDA_LAUNCHER int launch_bwd(const Problem& pr_in, const void* value, const int64_t* shapes, const int64_t* lsi,
                       const void* loc, const void* attn, const void* go, void* gv, void* gloc, void* gattn,
                       void* scratch, int flags, cudaStream_t st) {
+  Problem pr = pr_in;
   const size_t n_value = static_cast<size_t>(pr.N) * pr.S * pr.M * pr.D;
   constexpr bool k16 = sizeof(T) == 2;
   const bool use16 = k16 && !(flags & MSDA_BWD_GRAD_VALUE_FP32_ACCUM) && vec_supported<T>(pr);
-  // tiled kernels: one reduction per (destination row, tile) reaches the accumulator -- at most a few hundred adds per
-  // element on the coarsest level of a pyramid -- so a single copy per level (no buckets) keeps the fp16 error at ~2e-3
-  bool tiled = false;
-  if constexpr (k16) tiled = use16 && tiled_supported<T>(pr);
-  const int depth = tiled ? 0xffff : accum_depth(flags);
-  // a level can only be sparse (4*Lq*P <= H_l*W_l) if 4*Lq*P <= S: decided here, the levels themselves on the device
-  const bool sparse_direct = use16 && !(flags & MSDA_BWD_NO_SPARSE_DIRECT) && kSparseFactor * pr.Lq * pr.P <= pr.S;
-  // strided grad_value: the vector kernels with direct (fp32 / fp64-free) or fp16-bucket accumulation only
-  if (pr.strided() && (!vec_supported<T>(pr) || std::is_same<T, double>::value || (k16 && !use16))) return MSDA_ERR_BAD_STRIDE;
-  const int gstride = pr.grad_stride();
-  // 16-bit values accumulate in the scratch and grad_value is fully overwritten by the rounding pass, so only
-  // the buffer that receives the reductions is zeroed
-  cudaError_t e;
-  uint32_t* ctrl = nullptr;
-  __half* acc16 = nullptr;
-  if (!k16) {
+  // strided grad_value: the vector kernels only (fp32 values directly, 16-bit values in either accumulation mode)
+  if (pr.strided() && (!vec_supported<T>(pr) || std::is_same<T, double>::value)) return MSDA_ERR_BAD_STRIDE;
+
+  if constexpr (k16) {
+    if (!use16)      // fp32 accumulation asked for, or a head dim only the compatibility kernels cover
+      return run_bwd_fp32_accum<T>(pr, value, shapes, lsi, loc, attn, go, gv, gloc, gattn, static_cast<float*>(scratch),
+                                   accum_depth(flags), false, st);
+    const ScratchLayout sl = scratch_layout_16(pr.N, pr.S, pr.M, pr.D, pr.Lq, pr.L, pr.P, flags);
+    uint32_t* ctrl = static_cast<uint32_t*>(scratch);
+    char* payload = static_cast<char*>(scratch) + sl.payload_off;
+    // the density pass reads sampling locations: the fused pre-op (raw offsets) and the tiled kernels go unguarded
+    const bool guard = sl.guard && pr.ref == nullptr && !tiled_supported<T>(pr);
+    if (!guard) {
+      if (sl.counters_bytes != 0) {       // the accumulator does not follow the control block directly: clear it separately
+        const cudaError_t e0 = cudaMemsetAsync(scratch, 0, kF16CtrlBytes, st);
+        if (e0 != cudaSuccess) return static_cast<int>(e0);
+      }
+      return run_bwd_f16_accum<T>(pr, value, shapes, lsi, loc, attn, go, gv, gloc, gattn, ctrl,
+                                  reinterpret_cast<__half*>(payload), sl.counters_bytes == 0, flags, st);
+    }
+    // ---- cluster guard: count, then both pipelines; only the one ctrl[1] selects does any work ----
+    cudaError_t e = cudaMemsetAsync(scratch, 0, sl.payload_off, st);          // control block + counters
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const long long points = static_cast<long long>(pr.N) * pr.Lq * pr.M * pr.L * pr.P;
+    const bool sparse_direct = !(flags & MSDA_BWD_NO_SPARSE_DIRECT) && kSparseFactor * pr.Lq * pr.P <= pr.S;
+    const int dgrid = static_cast<int>(std::min<long long>((points + 255) / 256, static_cast<long long>(device_sm_count()) * 8));
+    msda_cluster_density_kernel<<<dgrid, 256, 0, st>>>(static_cast<const float*>(loc), shapes, lsi,
+                                                      reinterpret_cast<uint32_t*>(static_cast<char*>(scratch) + sl.counters_off),
+                                                      ctrl, points, sl.cells, pr.M, pr.Lq, pr.L, pr.P, accum_depth(flags),
+                                                      sparse_direct ? 1 : 0);
+    ++g_last_launches, ++g_total_launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+    pr.gate = ctrl + 1;
+    pr.gate_want = 0;
+    int rc = run_bwd_f16_accum<T>(pr, value, shapes, lsi, loc, attn, go, gv, gloc, gattn, ctrl,
+                                  reinterpret_cast<__half*>(payload), false, flags, st);
+    if (rc != 0) return rc;
+    pr.gate_want = 1;
+    return run_bwd_fp32_accum<T>(pr, value, shapes, lsi, loc, attn, go, gv, gloc, gattn, reinterpret_cast<float*>(payload),
+                                 accum_depth(flags), true, st);
+  } else {
+    // fp32 / fp64 values: reductions go straight into grad_value
+    cudaError_t e;
+    const int gstride = pr.grad_stride();
     if (gstride == pr.M * pr.D)
       e = cudaMemsetAsync(gv, 0, n_value * sizeof(T), st);
     else
       e = cudaMemset2DAsync(gv, static_cast<size_t>(gstride) * sizeof(T), 0, static_cast<size_t>(pr.M) * pr.D * sizeof(T),
                             static_cast<size_t>(pr.N) * pr.S, st);
-  } else if (use16) {
-    msda_zero_f16_buckets_kernel<<<148 * 8, 256, 0, st>>>(static_cast<uint4*>(scratch), kF16CtrlBytes / 16, shapes, lsi,
-                                                         sparse_direct ? static_cast<uint16_t*>(gv) : nullptr,
-                                                         pr.N, pr.S, pr.M, pr.D, pr.Lq, pr.L, pr.P, depth, gstride);
-    ++g_last_launches, ++g_total_launches;
-    e = cudaGetLastError();
-    ctrl = static_cast<uint32_t*>(scratch);
-    acc16 = reinterpret_cast<__half*>(static_cast<char*>(scratch) + kF16CtrlBytes);
-  } else {
-    e = cudaMemsetAsync(scratch, 0, n_value * sizeof(float), st);
-  }
-  if (e != cudaSuccess) return static_cast<int>(e);
-  if constexpr (k16) {
-    if (use16 && !tiled) {
-      const size_t n8 = static_cast<size_t>(pr.N) * pr.Lq * pr.M * pr.D / 8;     // D is a multiple of 16 here
-      const int grid = static_cast<int>(std::min<size_t>((n8 + 255) / 256, 148 * 8));
-      msda_absmax_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(go), n8, ctrl);
-      ++g_last_launches, ++g_total_launches;
-      e = cudaGetLastError();
-      if (e != cudaSuccess) return static_cast<int>(e);
-    }
-  }
-  int rc;
-  bool done = false;
-  if constexpr (k16) {
-    if (tiled) {
-      rc = launch_bwd_tiled<T>(pr, value, shapes, lsi, loc, attn, go, acc16, ctrl, gloc, gattn, depth, st);
-      done = true;
-    }
-  }
-  if constexpr (!std::is_same<T, double>::value) {
-    if (!done && vec_supported<T>(pr)) {
-      float* gv32 = k16 ? static_cast<float*>(scratch) : static_cast<float*>(gv);
-      void* gvd = sparse_direct ? gv : nullptr;                      // sparse levels add straight into grad_value
-      const int gvs = (k16 && !use16) ? pr.M * pr.D : gstride;       // the fp32 scratch of 16-bit values is dense
-      switch (pr.D) {
-        case 16: rc = launch_bwd_vec<T, 16>(pr, value, shapes, lsi, loc, attn, go, gv32, acc16, gvd, gvs, ctrl, gloc, gattn, use16, depth, st); break;
-        case 32: rc = launch_bwd_vec<T, 32>(pr, value, shapes, lsi, loc, attn, go, gv32, acc16, gvd, gvs, ctrl, gloc, gattn, use16, depth, st); break;
-        case 64: rc = launch_bwd_vec<T, 64>(pr, value, shapes, lsi, loc, attn, go, gv32, acc16, gvd, gvs, ctrl, gloc, gattn, use16, depth, st); break;
-        default: rc = launch_bwd_vec<T, 128>(pr, value, shapes, lsi, loc, attn, go, gv32, acc16, gvd, gvs, ctrl, gloc, gattn, use16, depth, st); break;
+    if (e != cudaSuccess) return static_cast<int>(e);
+    if constexpr (!std::is_same<T, double>::value) {
+      if (vec_supported<T>(pr)) {
+        float* gv32 = static_cast<float*>(gv);
+        const int depth = accum_depth(flags);
+        switch (pr.D) {
+          case 16: return launch_bwd_vec<T, 16>(pr, value, shapes, lsi, loc, attn, go, gv32, nullptr, nullptr, gstride, nullptr, gloc, gattn, false, depth, st);
+          case 32: return launch_bwd_vec<T, 32>(pr, value, shapes, lsi, loc, attn, go, gv32, nullptr, nullptr, gstride, nullptr, gloc, gattn, false, depth, st);
+          case 64: return launch_bwd_vec<T, 64>(pr, value, shapes, lsi, loc, attn, go, gv32, nullptr, nullptr, gstride, nullptr, gloc, gattn, false, depth, st);
+          default: return launch_bwd_vec<T, 128>(pr, value, shapes, lsi, loc, attn, go, gv32, nullptr, nullptr, gstride, nullptr, gloc, gattn, false, depth, st);
+        }
       }
-      done = true;
     }
-  }
-  if (!done) {
     if (pr.ref) return MSDA_ERR_FUSED_UNSUPPORTED;
     using Aux = typename Traits<T>::Aux;
     const int grid = (pr.total_pairs + kWarps - 1) / kWarps;
-    if constexpr (k16) {
-      msda_bwd_any_kernel<T, float><<<grid, kThreads, 0, st>>>(
-          static_cast<const T*>(value), shapes, lsi, static_cast<const Aux*>(loc), static_cast<const Aux*>(attn),
-          static_cast<const T*>(go), static_cast<float*>(scratch), static_cast<Aux*>(gloc), static_cast<Aux*>(gattn),
-          pr.S, pr.M, pr.D, pr.Lq, pr.L, pr.P, pr.total_pairs);
-    } else {
-      msda_bwd_any_kernel<T, T><<<grid, kThreads, 0, st>>>(
-          static_cast<const T*>(value), shapes, lsi, static_cast<const Aux*>(loc), static_cast<const Aux*>(attn),
-          static_cast<const T*>(go), static_cast<T*>(gv), static_cast<Aux*>(gloc), static_cast<Aux*>(gattn),
-          pr.S, pr.M, pr.D, pr.Lq, pr.L, pr.P, pr.total_pairs);
-    }
+    msda_bwd_any_kernel<T, T><<<grid, kThreads, 0, st>>>(
+        static_cast<const T*>(value), shapes, lsi, static_cast<const Aux*>(loc), static_cast<const Aux*>(attn),
+        static_cast<const T*>(go), static_cast<T*>(gv), static_cast<Aux*>(gloc), static_cast<Aux*>(gattn),
+        pr.S, pr.M, pr.D, pr.Lq, pr.L, pr.P, pr.total_pairs);
     ++g_last_launches, ++g_total_launches;
-    rc = static_cast<int>(cudaGetLastError());
+    return static_cast<int>(cudaGetLastError());
   }
-  if (rc != 0) return rc;
-  if constexpr (k16) {
-    if (use16) {
-      const size_t n8_img = static_cast<size_t>(pr.S) * pr.M * pr.D / 8;
-      const size_t want = (n8_img + 255) / 256, cap = std::max<size_t>(1, (148 * 16) / static_cast<size_t>(pr.N));
-      const dim3 grid(static_cast<unsigned>(std::min(want, cap)), static_cast<unsigned>(std::min(pr.N, 65535)));
-      msda_round_f16_buckets_kernel<T><<<grid, 256, 0, st>>>(acc16, static_cast<T*>(gv), shapes, lsi, ctrl, pr.N, pr.S,
-                                                            pr.M, pr.D, pr.Lq, pr.L, pr.P, depth, sparse_direct ? 1 : 0,
-                                                            gstride);
-      ++g_last_launches, ++g_total_launches;
-      rc = static_cast<int>(cudaGetLastError());
-    } else {
-      if ((n_value & 7) == 0) {
-        const size_t n8 = n_value / 8;
-        const int grid = static_cast<int>(std::min<size_t>((n8 + 255) / 256, 148 * 16));
-        msda_round_scratch_kernel<T><<<grid, 256, 0, st>>>(static_cast<const float*>(scratch), static_cast<T*>(gv), n8);
-      } else {
-        const int grid = static_cast<int>(std::min<size_t>((n_value + 255) / 256, 148 * 16));
-        msda_round_scratch_any_kernel<T><<<grid, 256, 0, st>>>(static_cast<const float*>(scratch), static_cast<T*>(gv), n_value);
-      }
-      ++g_last_launches, ++g_total_launches;
-      rc = static_cast<int>(cudaGetLastError());
-    }
-  }
-  return rc;
 }
 
 #ifdef MSDA_SPLIT_BUILD
@@ -1319,7 +1502,7 @@ extern "C" const char* msda_error_string(int code) {
     case MSDA_ERR_SCRATCH_TOO_SMALL: return "scratch buffer missing or too small";
     case MSDA_ERR_BAD_STRIDE:
       return "pixel stride must be >= M*D elements and a multiple of 16 bytes; strided tensors need the vector kernels "
-             "(head dim 16/32/64/128, not float64) and, for 16-bit values, the default accumulation mode";
+             "(head dim 16/32/64/128, not float64)";
     case MSDA_ERR_FUSED_UNSUPPORTED:
       return "fused pre-op needs float32/bfloat16/float16 values with head dim 16/32/64/128 and reference points of width 2 or 4";
     default: break;
@@ -1400,7 +1583,7 @@ extern "C" size_t msda_backward_scratch_bytes(int N, int S, int M, int D, int Lq
   if (N <= 0 || S <= 0 || M <= 0 || D <= 0 || Lq <= 0 || L <= 0 || P <= 0) return 0;
   const bool vec = (D == 16 || D == 32 || D == 64 || D == 128) &&
                    static_cast<unsigned long long>(S) * M * D * sizeof(float) < (1ull << 32);
-  if (!(flags & MSDA_BWD_GRAD_VALUE_FP32_ACCUM) && vec) return f16_scratch_bytes(N, S, M, D, Lq, L, P, accum_depth(flags));
+  if (!(flags & MSDA_BWD_GRAD_VALUE_FP32_ACCUM) && vec) return scratch_layout_16(N, S, M, D, Lq, L, P, flags).total;
   return static_cast<size_t>(N) * S * M * D * sizeof(float);
 }
 
