@@ -57,6 +57,11 @@ def parse_args():
                     help="train-step workloads: run every encoder layer as one fused autograd node (implies --fused-preop)")
     ap.add_argument("--shared-value-proj", action="store_true",
                     help="decoder-step workload: one stacked value_proj GEMM for all decoder layers (share_value_proj)")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="operator workloads: skip config.secondary (cold / warm L2, fp32, uniform locations, tiled kernels)")
+    ap.add_argument("--no-train-step", action="store_true",
+                    help="default workload: skip the embedded cfg5 2048^2 training step (config.train_step_cfg5)")
+    ap.add_argument("--train-step-batch", type=int, default=16, help="global batch of the embedded cfg5 training step")
     return ap.parse_args()
 
 
@@ -79,6 +84,24 @@ def ncu_traffic_bytes(kernel_key):
             return json.load(f).get(kernel_key)
     except Exception:
         return None
+
+
+def measured_red_ceiling_grows():
+    """L2 reduction ceiling for 64-byte packed-fp16 rows (G rows/s): the best `redg_bf16x8_64Brow` / f16x8 figure of the
+    committed microbenchmark record, or None."""
+    best = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "microbench_r01.jsonl")) as f:
+            for line in f:
+                line = line.strip()
+                if not line.startswith("{"):
+                    continue
+                d = json.loads(line)
+                if "64Brow" in str(d.get("test", "")) and str(d.get("test", "")).startswith("redg") and "Grows_per_s" in d:
+                    best = max(best or 0.0, float(d["Grows_per_s"]))
+    except Exception:
+        return None
+    return best
 
 
 class ClockSampler:
@@ -191,6 +214,69 @@ def run_reference(args):
     return 0
 
 
+def binding_resource(ab, bwd_avg_ms, dtype, tiled):
+    """What binds the direct backward: 4 corner-row reductions per sampled point against the measured
+    L2 reduction ceiling for 64-byte packed-fp16 rows (profiles/microbench_r01.jsonl)."""
+    import torch
+    if dtype == torch.float32 or tiled:
+        return None
+    ceiling = measured_red_ceiling_grows()
+    rows = 4 * ab["points"] / (bwd_avg_ms * 1e-3) / 1e9
+    return {"name": "L2 reduction path (red.global.add.noftz.v4.f16x2, 64-byte rows)", "achieved_Grows_per_s": rows,
+            "measured_ceiling_Grows_per_s": ceiling, "ceiling_source": "profiles/microbench_r01.jsonl (best redg_*_64Brow)",
+            "frac": rows / ceiling if ceiling else None}
+
+
+def secondary_rows(args, cfg, batch, dev, lib):
+    """One layer's forward and backward call of the extension-level API, CUDA events around each call (so the backward
+    includes its zero / max / rounding passes), median of 7 after 3 warm-ups:
+      cold  : 256 MiB written between calls (L2 flushed);  warm: the same inputs back to back (value of one image batch
+              does not fit the 126 MB L2 at this size, so `warm` mostly keeps loc / attn / the accumulator tail);
+      fp32  : the same geometry with float32 values;       uniform: sampling locations U(-0.05, 1.05) (no locality);
+      tiled : the opt-in tiled kernels (msda_set_tiled_mode(1)) on the encoder-like inputs."""
+    import torch
+    from vision_instance_seg_b200 import MultiScaleDeformableAttention as MSDA, workloads as W
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, cold):
+        ts = []
+        for r in range(10):
+            if cold:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            if r >= 3:
+                ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    def row(dtype, kind, tiled=False, cold=True):
+        maker = W.make_uniform_inputs if kind == "uniform" else W.make_encoder_inputs
+        v, ss, lsi, loc, attn = maker(cfg["shapes"], batch, dtype, seed=777, device=dev)
+        go = torch.randn(batch, loc.shape[1], v.shape[2] * v.shape[3], device=dev).to(dtype)
+        prev = lib.msda_set_tiled_mode(1 if tiled else 0)
+        try:
+            f = timed(lambda: MSDA.ms_deform_attn_forward(v, ss, lsi, loc, attn, 128), cold)
+            b = timed(lambda: MSDA.ms_deform_attn_backward(v, ss, lsi, loc, attn, go, 128), cold)
+        finally:
+            lib.msda_set_tiled_mode(prev)
+        pts = loc.numel() // 2
+        return {"forward_ms": f, "backward_ms": b, "points_per_s": pts / ((f + b) * 1e-3)}
+
+    dtype = cfg["dtype"]
+    out = {"what": "one layer, extension-level forward / backward call, CUDA events per call, median of 7",
+           "cold_l2": row(dtype, "encoder"), "warm_l2": row(dtype, "encoder", cold=False),
+           "uniform_locations": row(dtype, "uniform")}
+    if dtype != torch.float32:
+        out["fp32_values"] = row(torch.float32, "encoder")
+        out["tiled_kernels"] = row(dtype, "encoder", tiled=True)
+    del flush
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------------
@@ -272,6 +358,15 @@ def run_b200(args):
     records = _lib.profile_collect()
     fwd_ms = [t for t, k in records if k == 1]
     bwd_ms = [t for t, k in records if k == 2]
+    dots_ms = [t for t, k in records if k == 3]          # tiled mode (MSDA_B200_TILED=1): the backward is two kernels
+    scat_ms = [t for t, k in records if k == 4]
+    if not bwd_ms and dots_ms and len(dots_ms) == len(scat_ms):
+        bwd_ms = [a + b for a, b in zip(dots_ms, scat_ms)]
+
+    # ---- secondary measurements of the same operator: one layer's forward / backward call, event-timed ----
+    secondary = None
+    if not args.no_secondary and cfg["kind"] == "encoder":
+        secondary = secondary_rows(args, cfg, batch, dev, lib)
 
     # ---- end to end: pinned host -> device -> fwd+bwd -> pinned host, every layer of every step ----
     e2e = None
@@ -315,6 +410,32 @@ def run_b200(args):
                       "3 streams, batch cut into 4 pieces, triple-buffered staging)"}
         del host_in, host_out, pipe
 
+    # ---- BASELINE.json configs[4]: the 2048^2 training step, batch-sharded (strong scaling), on the same ranks ----
+    train_step = None
+    if args.workload == WORKLOAD and not args.no_train_step:
+        del sets
+        torch.cuda.empty_cache()
+        sub = argparse.Namespace(**vars(args))
+        sub.workload, sub.batch, sub.layers = "cfg5_train_step_2048", args.train_step_batch, None
+        sub.fused_layers, sub.fused_preop, sub.cuda_graph, sub.forward_only, sub.shared_value_proj = True, False, True, False, False
+        sub.no_e2e, sub.steps, sub.warmup = True, 3, 3
+        try:
+            tl = train_step_line(sub)
+        except Exception as exc:       # e.g. out of memory on a smaller GPU: report, do not lose the operator line
+            tl = {"error": f"{type(exc).__name__}: {exc}"[:300]} if rank == 0 else None
+        if tl is not None and "error" not in tl:
+            c = tl["config"]
+            train_step = {"workload": c["workload"], "global_batch": c["global_batch"], "per_gpu_batch": c["per_gpu_batch"],
+                          "n_gpus": tl["n_gpus"], "scaling": tl["scaling"], "ms_per_step": tl["ms_per_step"],
+                          "points_per_s": tl["value"], "points_per_step": c["points_per_step"],
+                          "grad_allreduce_bytes": c["grad_allreduce_bytes"], "grad_buckets": c["grad_buckets"],
+                          "fused_layers": c["fused_layers"], "cuda_graph": c["cuda_graph"], "gpu_launches_per_step": tl["gpu_launches"] // max(tl["steps"], 1),
+                          "msda_share_of_step": c.get("msda_share_of_step"), "msda_ms_per_step": c.get("msda_ms_per_step"),
+                          "peak_device_memory_gb": c["peak_device_memory_gb"], "final_loss": c["final_loss"],
+                          "note": "strong scaling: efficiency(N) = ms_per_step(1) / (N * ms_per_step(N)); the driver computes it"}
+        else:
+            train_step = tl
+
     if rank != 0:
         return 0
 
@@ -338,10 +459,10 @@ def run_b200(args):
                     "backward_points_per_s": ab["points"] / (bwd_avg * 1e-3),
                     # what actually binds the backward: 4 corner-row reductions per sampled point
                     # against the measured L2 reduction ceiling for 64-byte packed-fp16 rows (profiles/microbench_r01.jsonl)
-                    "binding_resource": {"name": "L2 reduction path (red.global.add.noftz.v4.f16x2, 64-byte rows)",
-                                         "achieved_Grows_per_s": 4 * ab["points"] / (bwd_avg * 1e-3) / 1e9,
-                                         "measured_ceiling_Grows_per_s": 85.0,
-                                         "frac": 4 * ab["points"] / (bwd_avg * 1e-3) / 85.0e9} if dtype != torch.float32 else None}
+                    "binding_resource": binding_resource(ab, bwd_avg, dtype, bool(dots_ms))}
+        if dots_ms:
+            roofline["kernel"] = "msda_bwd_dots_tiled + msda_bwd_scatter_tiled (MSDA_B200_TILED=1)"
+            roofline["tiled_kernels_ms"] = {"dots": statistics.mean(dots_ms), "scatter": statistics.mean(scat_ms)}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -360,7 +481,9 @@ def run_b200(args):
                    "levels": cfg["shapes"], "queries": Lq, "heads": M, "head_dim": Dh, "points": P,
                    "aux_dtype": "f32", "points_per_step_per_gpu": pts_per_step, "parallelism": f"dp{world}",
                    "grad_allreduce_bytes": D.ENCODER_GRAD_ELEMENTS * 4 if world > 1 else 0, "cpu_binding_rank0": numa,
-                   "l2_policy": f"{layers} independent input sets ({layers * (ab['fwd'] + ab['bwd']) / 1e9:.1f} GB touched per step) >> 126 MB L2; no flush needed"},
+                   "l2_policy": f"{layers} independent input sets ({layers * (ab['fwd'] + ab['bwd']) / 1e9:.1f} GB touched per step) >> 126 MB L2; no flush needed",
+                   "tiled_kernels": os.environ.get("MSDA_B200_TILED") == "1", "secondary": secondary,
+                   "train_step_cfg5": train_step},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)
@@ -371,6 +494,14 @@ def run_b200(args):
 # training-step workloads (BASELINE.json configs[4]): 6-layer encoder, batch-sharded, gradient all-reduce, AdamW
 # ------------------------------------------------------------------------------------------------------
 def run_train_step(args):
+    line = train_step_line(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def train_step_line(args):
+    """Runs the training-step workload on every rank; returns the JSON line (a dict) on rank 0, None elsewhere."""
     import torch
     import vision_instance_seg_b200 as pkg
     from vision_instance_seg_b200 import _lib, distributed as D, workloads as W
@@ -530,7 +661,25 @@ def run_train_step(args):
     records = _lib.profile_collect()
     fwd_ms = [t for t, k in records if k == 1]
     bwd_ms = [t for t, k in records if k == 2]
+    if not bwd_ms:                              # tiled kernels: dots + scatter make one backward
+        d3, d4 = [t for t, k in records if k == 3], [t for t, k in records if k == 4]
+        bwd_ms = [a + b for a, b in zip(d3, d4)]
     final_loss = float(loss.detach())
+    if args.cuda_graph and not (fwd_ms or bwd_ms):
+        # kernels inside a replayed graph cannot be event-timed: time the sampling kernels of one eager step of the same body
+        lib.msda_profile_enable(1)
+        step_body(srcs)
+        torch.cuda.synchronize(dev)
+        lib.msda_profile_enable(0)
+        eager = _lib.profile_collect()
+        fwd_ms = [t for t, k in eager if k == 1]
+        bwd_ms = [t for t, k in eager if k == 2]
+        if not bwd_ms:
+            d3, d4 = [t for t, k in eager if k == 3], [t for t, k in eager if k == 4]
+            bwd_ms = [a + b for a, b in zip(d3, d4)]
+        msda_ms_per_step = sum(fwd_ms) + sum(bwd_ms)
+    else:
+        msda_ms_per_step = (sum(bwd_ms) + sum(fwd_ms)) / args.steps if (bwd_ms or fwd_ms) else None
 
     e2e = None
     if not args.no_e2e:
@@ -548,8 +697,11 @@ def run_train_step(args):
                        "memory every step, loss copied back") if decoder_step else
                       ("MSDeformAttnTransformerEncoderOnly.forward/backward + GradientBuckets + AdamW; feature pyramid copied "
                        "from pinned host memory every step, loss copied back")}
+    peak_mem = round(torch.cuda.max_memory_allocated(dev) / 1e9, 2)
+    del enc, opt, buckets, srcs, graph
+    torch.cuda.empty_cache()
     if rank != 0:
-        return 0
+        return None
     peak, peak_src = measured_peak_gbs()
     ab = W.algorithmic_bytes(count, S, cfg["queries"] if decoder_step else S, M, C // M, L, P, 2)
     if args.fused_preop:        # sampling locations / attention weights never reach HBM: raw offsets + logits instead (same sizes)
@@ -560,7 +712,7 @@ def run_train_step(args):
         roofline = {"bound": "hbm", "kernel": "msda_fwd (forward gather)", "achieved": ab["fwd"] / (fwd_avg * 1e-3) / 1e9,
                     "peak": peak, "unit": "GB/s", "frac": ab["fwd"] / (fwd_avg * 1e-3) / 1e9 / peak, "traffic": None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": ab["fwd"], "avg_launch_ms": fwd_avg,
-                    "launches_timed": len(fwd_ms), "msda_share_of_step": sum(fwd_ms) / args.steps / ms_per_step}
+                    "launches_timed": len(fwd_ms), "msda_share_of_step": msda_ms_per_step / ms_per_step}
     if bwd_ms:
         bwd_avg, fwd_avg = statistics.mean(bwd_ms), statistics.mean(fwd_ms)
         roofline = {"bound": "hbm", "kernel": "msda_bwd (backward gather + grad_value scatter)",
@@ -569,7 +721,7 @@ def run_train_step(args):
                     "algorithmic_bytes_per_launch": ab["bwd"], "avg_launch_ms": bwd_avg, "launches_timed": len(bwd_ms),
                     "forward": {"avg_launch_ms": fwd_avg, "algorithmic_bytes_per_launch": ab["fwd"],
                                 "frac": ab["fwd"] / (fwd_avg * 1e-3) / 1e9 / peak},
-                    "msda_share_of_step": (sum(bwd_ms) + sum(fwd_ms)) / args.steps / ms_per_step}
+                    "msda_share_of_step": msda_ms_per_step / ms_per_step}
     line = {
         "metric": METRIC, "value": pts_per_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -582,12 +734,13 @@ def run_train_step(args):
                    "optimizer": "AdamW(fused)", "autocast": "bf16",
                    "parallelism": f"dp{world}", "grad_allreduce_bytes": int(buckets.flat.numel() * 4) if world > 1 else 0,
                    "grad_buckets": len(buckets.slices), "points_per_step": pts_per_step, "final_loss": final_loss,
-                   "peak_device_memory_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2),
+                   "peak_device_memory_gb": peak_mem,
+                   "msda_share_of_step": msda_ms_per_step / ms_per_step if msda_ms_per_step else None,
+                   "msda_ms_per_step": msda_ms_per_step,
                    "l2_policy": "activations of one step (GBs) >> 126 MB L2; no flush needed"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": None,
     }
-    print(json.dumps(line), flush=True)
-    return 0
+    return line
 
 
 def _shutdown():

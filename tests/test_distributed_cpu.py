@@ -85,3 +85,32 @@ def test_shard_batch_covers_everything():
                 pos += c
     with pytest.raises(ValueError):
         shard_batch(4, 2, 2)
+
+
+def test_gradient_buckets_survive_zero_grad_set_to_none():
+    """after ``zero_grad(set_to_none=True)`` autograd creates fresh ``.grad`` tensors outside the bucket; the
+    hook must adopt them (copy into the slice, re-install the view) instead of reducing a slice of zeros."""
+    import torch
+    from vision_instance_seg_b200.distributed import GradientBuckets
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    buckets = GradientBuckets([list(net[1].parameters()), list(net[0].parameters())], device="cpu")
+    x = torch.randn(5, 4)
+    net(x).square().sum().backward()
+    buckets.wait()
+    want = [p.grad.clone() for p in net.parameters()]
+    assert all(p.grad.data_ptr() == buckets._view_of[id(p)].data_ptr() for p in net.parameters())
+    net.zero_grad(set_to_none=True)                 # what optimizers and modules do by default
+    buckets.zero()
+    assert all(p.grad is not None and p.grad.data_ptr() == buckets._view_of[id(p)].data_ptr() for p in net.parameters())
+    net.zero_grad(set_to_none=True)                 # ... and without calling zero() afterwards
+    buckets._pending = list(buckets._sizes)
+    net(x).square().sum().backward()
+    buckets.wait()
+    for p, w in zip(net.parameters(), want):
+        assert p.grad.data_ptr() == buckets._view_of[id(p)].data_ptr()
+        assert torch.allclose(p.grad, w)
+    off = 0
+    for p in list(net[1].parameters()) + list(net[0].parameters()):
+        assert torch.allclose(buckets.flat[off:off + p.numel()].view_as(p), p.grad)
+        off += p.numel()

@@ -476,3 +476,11 @@ def test_config4_full_batch_against_the_oracle_per_image(ops):
     worst = _compare_per_image(ops, v, ss, lsi, loc, attn, go)
     for name, err in worst.items():
         assert err < 2e-2, f"{name}: {err:.3e}"
+
+
+@pytest.mark.parametrize("dtype,D,L,P", [(torch.bfloat16, 16, 2, 80), (torch.float32, 32, 3, 200), (torch.float16, 128, 1, 700)])
+def test_many_points_per_query_run_on_the_compatibility_kernels(ops, dtype, D, L, P):
+    """the vector kernels stage a warp's L*P rows in shared memory, which caps L*P (~130 for 16-bit D = 16,
+    ~530 for fp32 D = 32); upstream has no such limit, so larger L*P must run (on the any-D kernels), not fail."""
+    shapes = [(9, 7), (5, 4), (3, 3)][:L]
+    check(ops, random_problem(1, 2, D, 5, shapes, P, seed=31), dtype, tol=TOL[dtype] if dtype != torch.float16 else 5e-3)

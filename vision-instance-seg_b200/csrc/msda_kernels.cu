@@ -1033,11 +1033,27 @@ static int validate(const Problem& pr, int dtype, int im2col_step) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// vector kernels: head dims with power-of-two lane groups, and per-image byte offsets that fit 32 bits
+// shared memory the vector kernels stage per CTA (the backward's is the larger one; see vec_smem_bytes): L*P rows of a
+// warp's pairs must fit next to each other, which caps L*P at ~130 (16-bit, D = 16) ... ~530 (fp32, D = 32)
+constexpr size_t kVecSmemLimit = 200 * 1024;
+static size_t vec_smem_bytes_rt(int D, size_t elem_bytes, int L, int P, bool fused) {
+  const int G = static_cast<int>(D * elem_bytes / 16);
+  const int GPW = 32 / (G > 0 ? G : 1);
+  const int LP = L * P;
+  return static_cast<size_t>(kWarps) * GPW * (loc_row_stride(LP) + (fused ? 2 : 1) * attn_row_stride(LP) + (fused ? 4 * L : 0)) *
+         sizeof(float);
+}
+
+// vector kernels: head dims with power-of-two lane groups, per-image byte offsets that fit 32 bits, and staged rows that
+// fit shared memory; everything else (upstream has no such limits) runs on the compatibility kernels
+static bool vec_supported_rt(int S, int M, int D, int L, int P, size_t elem_bytes, long long row_elems, bool fused) {
+  const bool d_ok = D == 16 || D == 32 || D == 64 || D == 128;
+  if (!d_ok) return false;
+  if (static_cast<unsigned long long>(S) * static_cast<unsigned long long>(row_elems) * sizeof(float) >= (1ull << 32)) return false;
+  return vec_smem_bytes_rt(D, elem_bytes, L, P, fused) <= kVecSmemLimit;
+}
 template <typename T> static bool vec_supported(const Problem& pr) {
-  const bool d_ok = pr.D == 16 || pr.D == 32 || pr.D == 64 || pr.D == 128;
-  const unsigned long long row = static_cast<unsigned long long>(std::max(pr.value_stride(), pr.grad_stride()));
-  return d_ok && static_cast<unsigned long long>(pr.S) * row * sizeof(float) < (1ull << 32);
+  return vec_supported_rt(pr.S, pr.M, pr.D, pr.L, pr.P, sizeof(T), std::max(pr.value_stride(), pr.grad_stride()), pr.ref != nullptr);
 }
 
 // per warp: GPW rows of loc (2*LP + 4 floats) and attn (LP + 4); fused backward adds a gattn row per pair; fused kernels
@@ -1066,7 +1082,7 @@ static int launch_fwd_vec_impl(const Problem& pr, const void* value, const int64
   const int per_cta = kWarps * GPW;
   const int grid = (pr.total_pairs + per_cta - 1) / per_cta;
   const size_t smem = vec_smem_bytes<T, D>(pr.L, pr.P, FUSED, false);
-  if (smem > 200 * 1024) return MSDA_ERR_BAD_SHAPE;
+  if (smem > kVecSmemLimit) return MSDA_ERR_BAD_SHAPE;       // not reached: vec_supported() sends such shapes elsewhere
   cudaError_t e = allow_smem(msda_fwd_vec_kernel<T, D, FUSED, AT>, smem);
   if (e != cudaSuccess) return static_cast<int>(e);
   ScopedKernelTimer timer(MSDA_KERNEL_FORWARD, st);
@@ -1199,7 +1215,7 @@ static int launch_bwd_vec_impl(const Problem& pr, const void* value, const int64
                                const uint32_t* ctrl, void* gloc, void* gattn, bool use16, int depth, cudaStream_t st) {
   constexpr int GPW = 32 / (D / (16 / static_cast<int>(sizeof(T))));
   const size_t smem = vec_smem_bytes<T, D>(pr.L, pr.P, FUSED, true);
-  if (smem > 200 * 1024) return MSDA_ERR_BAD_SHAPE;
+  if (smem > kVecSmemLimit) return MSDA_ERR_BAD_SHAPE;       // not reached: vec_supported() sends such shapes elsewhere
   const int per_cta = kWarps * GPW;
   const int grid = (pr.total_pairs + per_cta - 1) / per_cta;
   cudaError_t e;
@@ -1581,8 +1597,7 @@ extern "C" int msda_forward(const void* value, const int64_t* spatial_shapes, co
 extern "C" size_t msda_backward_scratch_bytes(int N, int S, int M, int D, int Lq, int L, int P, int value_dtype, int flags) {
   if (value_dtype != MSDA_BF16 && value_dtype != MSDA_F16) return 0;
   if (N <= 0 || S <= 0 || M <= 0 || D <= 0 || Lq <= 0 || L <= 0 || P <= 0) return 0;
-  const bool vec = (D == 16 || D == 32 || D == 64 || D == 128) &&
-                   static_cast<unsigned long long>(S) * M * D * sizeof(float) < (1ull << 32);
+  const bool vec = vec_supported_rt(S, M, D, L, P, 2, static_cast<long long>(M) * D, false);
   if (!(flags & MSDA_BWD_GRAD_VALUE_FP32_ACCUM) && vec) return scratch_layout_16(N, S, M, D, Lq, L, P, flags).total;
   return static_cast<size_t>(N) * S * M * D * sizeof(float);
 }

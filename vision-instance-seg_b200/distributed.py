@@ -139,18 +139,21 @@ class GradientBuckets:
         self.device = torch.device(device) if device is not None else params[0].device
         dtype = params[0].dtype
         self.flat = torch.zeros(sum(p.numel() for p in params), dtype=dtype, device=self.device)
-        self.slices, self._group_of, self._handles = [], {}, []
+        self.slices, self._group_of, self._handles, self._view_of = [], {}, [], {}
         off = 0
         for gi, g in enumerate(groups):
             start = off
             for p in g:
-                p.grad = self.flat[off:off + p.numel()].view_as(p)
+                view = self.flat[off:off + p.numel()].view_as(p)
+                p.grad = view
+                self._view_of[id(p)] = view
                 off += p.numel()
                 self._group_of[id(p)] = gi
                 self._handles.append(p.register_post_accumulate_grad_hook(self._on_grad))
             self.slices.append((start, off))
         self._sizes = [len(g) for g in groups]
         self._pending = list(self._sizes)
+        self._params = params
         self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
         self.launched = 0
         # True while the side stream holds reductions the main stream has not joined yet.  Joining only then keeps the
@@ -162,6 +165,15 @@ class GradientBuckets:
         return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
     def _on_grad(self, p):
+        # `optimizer.zero_grad()` / `module.zero_grad()` default to set_to_none=True: autograd then hands the parameter a
+        # fresh `.grad` tensor that is NOT a view into the bucket, and reducing the bucket slice would silently average
+        # zeros.  Adopt such a gradient: copy it into the slice and re-install the view (callers should use `zero()`).
+        view = self._view_of[id(p)]
+        if p.grad is None:
+            raise RuntimeError("GradientBuckets: post-accumulate hook fired without a gradient")
+        if p.grad.data_ptr() != view.data_ptr():
+            view.copy_(p.grad)
+            p.grad = view
         gi = self._group_of[id(p)]
         self._pending[gi] -= 1
         if self._pending[gi] == 0:
@@ -196,10 +208,18 @@ class GradientBuckets:
             self._side_pending = False
 
     def zero(self):
+        """Clear the bucket for the next step (use this instead of ``zero_grad(set_to_none=True)``; gradients that were
+        detached from the bucket anyway are re-attached here and by the hook)."""
         self._join()
         self.flat.zero_()
+        self._reattach()
         self._pending = list(self._sizes)
         self.launched = 0
+
+    def _reattach(self):
+        for p in self._params:
+            if p.grad is None or p.grad.data_ptr() != self._view_of[id(p)].data_ptr():
+                p.grad = self._view_of[id(p)]
 
     def remove_hooks(self):
         for h in self._handles:

@@ -112,12 +112,14 @@ class MSDeformAttn(nn.Module):
         """
         N, Len_q, _ = query.shape
         N, Len_in, _ = input_flatten.shape
-        # upstream's assert reads the shapes back from the device (a host sync); the verdict is remembered per
-        # (shape tensor, version, Len_in), so steady-state steps -- and CUDA-graph captures after a warm-up -- do not sync
-        shapes_key = (input_spatial_shapes.data_ptr(), input_spatial_shapes._version, Len_in)
-        if self.__dict__.get("_shapes_checked") != shapes_key:
+        # upstream's assert reads the shapes back from the device (a host sync); the verdict is remembered for the very
+        # tensor OBJECT that passed (kept alive here, so its storage cannot be recycled for other contents), its version
+        # counter and Len_in: steady-state steps -- and CUDA-graph captures after a warm-up -- do not sync, and a new
+        # shape tensor, an in-place edit or another input length is checked again
+        chk = self.__dict__.get("_shapes_checked")
+        if chk is None or chk[0] is not input_spatial_shapes or chk[1] != input_spatial_shapes._version or chk[2] != Len_in:
             assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
-            self.__dict__["_shapes_checked"] = shapes_key
+            self.__dict__["_shapes_checked"] = (input_spatial_shapes, input_spatial_shapes._version, Len_in)
 
         stacked = None
         if self._stacked_value is not None and input_flatten.is_cuda:

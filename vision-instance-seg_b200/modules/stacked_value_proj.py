@@ -138,6 +138,7 @@ class StackedValueProj:
     def _clear(self):
         self._src = self._mask = self._views = self._value_all = self._shared = self._key = None
         self._served = 0
+        self._last_index = -1
 
     @staticmethod
     def _tensor_key(t: Optional[torch.Tensor]):
@@ -173,13 +174,19 @@ class StackedValueProj:
     def value_for(self, index: int, input_flatten: torch.Tensor, input_padding_mask: Optional[torch.Tensor]):
         """Layer ``index``'s (view, value_all, shared); the stacked GEMM runs when a forward pass presents a memory tensor
         (or mask) that differs from the cached one, and the cache is dropped once all K layers have been served."""
-        key = (self._tensor_key(input_flatten), self._tensor_key(input_padding_mask), torch.is_grad_enabled())
-        if self._views is None or key != self._key:
+        # the key also covers the projection weights (an optimizer step in between bumps their version counters), and a
+        # layer index that does not advance means a new forward pass began -- e.g. after a pass that served fewer than K
+        # layers (exception, early exit, pruned layers): never hand out a projection computed with stale weights or
+        # whose autograd graph has been freed
+        wkey = tuple(t._version for m in self.modules for t in (m.value_proj.weight, m.value_proj.bias))
+        key = (self._tensor_key(input_flatten), self._tensor_key(input_padding_mask), torch.is_grad_enabled(), wkey)
+        if self._views is None or key != self._key or index <= self._last_index:
             self._clear()
             self._views, self._value_all, self._shared = self.project(input_flatten, input_padding_mask)
             self._src, self._mask = input_flatten, input_padding_mask        # keep them alive: the key holds addresses
             self._key = key
         out = (self._views[index], self._value_all, self._shared)
+        self._last_index = index
         self._served += 1
         if self._served >= self.K:
             self._clear()
