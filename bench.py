@@ -625,10 +625,16 @@ def train_step_line(args):
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):           # warm up off the default stream (allocator, cuBLAS workspaces, NCCL)
-            for _ in range(3):
+            for i in range(3):
+                # kernels inside a replayed graph cannot be event-timed: time the sampling kernels of the last eager
+                # warm-up step of the same body instead (config.msda_ms_per_step)
+                lib.msda_profile_enable(1 if i == 2 else 0)
                 step_body(srcs)
+            lib.msda_profile_enable(0)
         torch.cuda.current_stream(dev).wait_stream(side)
         barrier()
+        eager_records = _lib.profile_collect()
+        torch.cuda.empty_cache()                # the capture allocates its own pool: hand the warm-up's cached blocks back first
         launches_a = lib.msda_total_launch_count()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
@@ -666,12 +672,7 @@ def train_step_line(args):
         bwd_ms = [a + b for a, b in zip(d3, d4)]
     final_loss = float(loss.detach())
     if args.cuda_graph and not (fwd_ms or bwd_ms):
-        # kernels inside a replayed graph cannot be event-timed: time the sampling kernels of one eager step of the same body
-        lib.msda_profile_enable(1)
-        step_body(srcs)
-        torch.cuda.synchronize(dev)
-        lib.msda_profile_enable(0)
-        eager = _lib.profile_collect()
+        eager = eager_records
         fwd_ms = [t for t, k in eager if k == 1]
         bwd_ms = [t for t, k in eager if k == 2]
         if not bwd_ms:
@@ -698,6 +699,7 @@ def train_step_line(args):
                       ("MSDeformAttnTransformerEncoderOnly.forward/backward + GradientBuckets + AdamW; feature pyramid copied "
                        "from pinned host memory every step, loss copied back")}
     peak_mem = round(torch.cuda.max_memory_allocated(dev) / 1e9, 2)
+    grad_bytes, n_buckets = int(buckets.flat.numel() * 4) if world > 1 else 0, len(buckets.slices)
     del enc, opt, buckets, srcs, graph
     torch.cuda.empty_cache()
     if rank != 0:
@@ -732,8 +734,8 @@ def train_step_line(args):
                    "fused_preop": bool(args.fused_preop or args.fused_layers), "fused_layers": bool(args.fused_layers),
                    "cuda_graph": bool(args.cuda_graph), "forward_only": bool(args.forward_only),
                    "optimizer": "AdamW(fused)", "autocast": "bf16",
-                   "parallelism": f"dp{world}", "grad_allreduce_bytes": int(buckets.flat.numel() * 4) if world > 1 else 0,
-                   "grad_buckets": len(buckets.slices), "points_per_step": pts_per_step, "final_loss": final_loss,
+                   "parallelism": f"dp{world}", "grad_allreduce_bytes": grad_bytes,
+                   "grad_buckets": n_buckets, "points_per_step": pts_per_step, "final_loss": final_loss,
                    "peak_device_memory_gb": peak_mem,
                    "msda_share_of_step": msda_ms_per_step / ms_per_step if msda_ms_per_step else None,
                    "msda_ms_per_step": msda_ms_per_step,
