@@ -227,6 +227,60 @@ def binding_resource(ab, bwd_avg_ms, dtype, tiled):
             "frac": rows / ceiling if ceiling else None}
 
 
+def e2e_fused_16bit(args, cfg, batch, layers, dev, world, bucket, barrier, pts_per_step):
+    """`e2e` once more through HostPipeline(fused=True): operands (value, reference_points, raw sampling offsets and
+    attention logits in the value dtype, grad_output) start in pinned host memory, results (output, grad_value, grad of
+    offsets / logits in the value dtype) end there."""
+    import torch
+    from vision_instance_seg_b200 import distributed as D, workloads as W
+    from vision_instance_seg_b200.host_pipeline import HostPipeline
+    dtype = cfg["dtype"]
+    shapes = cfg["shapes"]
+    ss = W.make_spatial_shapes(shapes, dev)
+    lsi = W.make_level_start_index(ss)
+    L, S = len(shapes), int(ss.prod(1).sum())
+    M, Dh, P = 8, 32, 4
+    g = torch.Generator().manual_seed(4242)
+    value = torch.randn(batch, S, M, Dh, generator=g).to(dtype).pin_memory()
+    ref = W.get_reference_points(ss.cpu(), torch.ones(batch, L, 2)).contiguous().pin_memory()         # (N, S, L, 2) fp32
+    off = (torch.randn(batch, S, M, L, P, 2, generator=g) * 2.0).to(dtype).pin_memory()               # pixels, raw
+    logits = torch.randn(batch, S, M, L * P, generator=g).to(dtype).pin_memory()
+    go = torch.randn(batch, S, M * Dh, generator=g).to(dtype).pin_memory()
+    host_in = [value, ref, off, logits, go]
+    host_out = [torch.empty((batch, S, M * Dh), dtype=dtype).pin_memory(), torch.empty(tuple(value.shape), dtype=dtype).pin_memory(),
+                torch.empty(tuple(off.shape), dtype=dtype).pin_memory(), torch.empty(tuple(logits.shape), dtype=dtype).pin_memory()]
+    h2d = sum(t.numel() * t.element_size() for t in host_in) * layers
+    d2h = sum(t.numel() * t.element_size() for t in host_out) * layers
+    pipe = HostPipeline(ss, lsi, dev, fused=True)
+
+    def step():
+        for _ in range(layers):
+            pipe.submit(host_in, host_out)
+        if bucket is not None:
+            bucket.allreduce_async()
+
+    step()
+    pipe.wait_all()
+    if bucket is not None:
+        bucket.wait()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.e2e_steps):
+        step()
+    pipe.wait_all()
+    if bucket is not None:
+        bucket.wait()
+    e1.record()
+    barrier()
+    ms = D.max_over_ranks(e0.elapsed_time(e1), dev) / args.e2e_steps
+    assert torch.isfinite(host_out[0].float()).all()
+    return {"value": pts_per_step * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "pcie_gbs_per_rank": {"h2d": h2d / (ms * 1e-3) / 1e9, "d2h": d2h / (ms * 1e-3) / 1e9},
+            "api": "HostPipeline(fused=True).submit: msda_fused_forward / msda_fused_backward, offsets / logits and their "
+                   "gradients in the value dtype"}
+
+
 def secondary_rows(args, cfg, batch, dev, lib):
     """One layer's forward and backward call of the extension-level API, CUDA events around each call (so the backward
     includes its zero / max / rounding passes), median of 7 after 3 warm-ups:
@@ -406,9 +460,17 @@ def run_b200(args):
         assert torch.equal(ref_out.cpu(), host_out[0]), "e2e pipeline result differs from the device-resident path"
         e2e = {"value": pts_per_step * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": args.e2e_steps,
+               "pcie_gbs_per_rank": {"h2d": h2d / (e2e_ms * 1e-3) / 1e9, "d2h": d2h / (e2e_ms * 1e-3) / 1e9},
                "api": "HostPipeline.submit (pinned host operands -> ms_deform_attn_forward/backward -> pinned host results; "
                       "3 streams, batch cut into 4 pieces, triple-buffered staging)"}
         del host_in, host_out, pipe
+        # second figure: the fused pre-op entry points with 16-bit offsets / logits (what the Linears emit under
+        # autocast): 6 instead of 12 bytes of auxiliary operands per sampled point in each direction
+        if dtype != torch.float32 and cfg["kind"] == "encoder":
+            try:
+                e2e["fused_16bit_aux"] = e2e_fused_16bit(args, cfg, batch, layers, dev, world, bucket, barrier, pts_per_step)
+            except Exception as exc:
+                e2e["fused_16bit_aux"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
 
     # ---- BASELINE.json configs[4]: the 2048^2 training step, batch-sharded (strong scaling), on the same ranks ----
     train_step = None

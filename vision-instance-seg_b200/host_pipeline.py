@@ -18,8 +18,17 @@ from . import MultiScaleDeformableAttention as MSDA
 
 
 class HostPipeline:
+    """``fused=False`` (default): the upstream extension API, operands (value, sampling_locations, attention_weights,
+    grad_output) -> results (output, grad_value, grad_sampling_loc, grad_attn_weight).
+
+    ``fused=True``: the fused pre-op entry points (include/msda_b200.h ``msda_fused_forward / backward``), operands (value,
+    reference_points, sampling_offsets, attn_logits, grad_output) -> results (output, grad_value, grad_sampling_offsets,
+    grad_attn_logits).  With offsets / logits in the 16-bit value dtype -- what the two Linears emit under autocast -- the
+    per-point auxiliary traffic over PCIe is 6 bytes each way instead of 12."""
+
     def __init__(self, spatial_shapes: torch.Tensor, level_start_index: torch.Tensor, device, im2col_step: int = 128,
-                 depth: int = 3, chunks: int = 4):
+                 depth: int = 3, chunks: int = 4, fused: bool = False):
+        self.fused = bool(fused)
         self.device = torch.device(device)
         self.shapes = spatial_shapes.to(self.device, torch.int64).contiguous()
         self.lsi = level_start_index.to(self.device, torch.int64).contiguous()
@@ -38,8 +47,9 @@ class HostPipeline:
         self.d2h_bytes = 0
 
     def submit(self, host_in, host_out):
-        """host_in = (value, sampling_locations, attention_weights, grad_output) pinned CPU tensors;
-        host_out = (output, grad_value, grad_sampling_loc, grad_attn_weight) pinned CPU tensors to fill."""
+        """host_in = (value, sampling_locations, attention_weights, grad_output) pinned CPU tensors -- or, with
+        ``fused=True``, (value, reference_points, sampling_offsets, attn_logits, grad_output); host_out = (output,
+        grad_value, grad of the location-like operand, grad of the weight-like operand) pinned CPU tensors to fill."""
         n = host_in[0].shape[0]
         pieces = min(self.chunks, n)
         base, rem = divmod(n, pieces)
@@ -66,9 +76,15 @@ class HostPipeline:
                 self.ev_in[k].record(self.s_in)
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(self.ev_in[k])
-                v, loc, attn, go = dev_in
-                out = MSDA.ms_deform_attn_forward(v, self.shapes, self.lsi, loc, attn, self.im2col_step)
-                gv, gl, ga = MSDA.ms_deform_attn_backward(v, self.shapes, self.lsi, loc, attn, go, self.im2col_step)
+                if self.fused:
+                    v, ref, off, logits, go = dev_in
+                    out = MSDA.ms_deform_attn_fused_forward(v, self.shapes, self.lsi, ref, off, logits, self.im2col_step)
+                    gv, gl, ga = MSDA.ms_deform_attn_fused_backward(v, self.shapes, self.lsi, ref, off, logits, go,
+                                                                    self.im2col_step)
+                else:
+                    v, loc, attn, go = dev_in
+                    out = MSDA.ms_deform_attn_forward(v, self.shapes, self.lsi, loc, attn, self.im2col_step)
+                    gv, gl, ga = MSDA.ms_deform_attn_backward(v, self.shapes, self.lsi, loc, attn, go, self.im2col_step)
                 self.ev_run[k].record(self.s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_run[k])
