@@ -53,6 +53,15 @@ constexpr int kGroups = kThreadsT / 8;     // 8-lane groups per CTA
 constexpr int kPF = 4;                     // points per thread per chunk
 constexpr int kChunkPts = kThreadsT * kPF; // record slots per chunk
 constexpr int kQC = 64;                    // queries per chunk (at most; kChunkPts / LP8 if that is smaller)
+// Window fill: 16-byte cp.async (0, default) or one TMA bulk copy per window pixel (1: fill_windows_bulk).  Measured at
+// cfg3 with -DMSDA_TILED_FILL_BULK=1: forward 1.24 ms against 0.99 ms, dots 1.50 against 1.25 ms.  UBLKCP takes its
+// operands from uniform registers, so per-lane copies compile to an ELECT / R2UR loop of ~8 instructions per 64-byte
+// copy (11 K warp-instructions per work item against 1.9 K for the cp.async loop); only a tensor-map copy (one
+// instruction per level) would pay, and that needs the level shapes on the host.
+#ifndef MSDA_TILED_FILL_BULK
+#define MSDA_TILED_FILL_BULK 0
+#endif
+constexpr bool kFillBulk = MSDA_TILED_FILL_BULK != 0;
 constexpr uint32_t kRowFallback = 0xFFFFu; // record marker: footprint outside the windows and no overflow slot left
 constexpr uint32_t kRowsNull = static_cast<uint32_t>(kZeroRow) | (static_cast<uint32_t>(kZeroRow) << 16);
 
@@ -67,6 +76,7 @@ struct Geom {
   int wx0[kMaxL], wy0[kMaxL];                 // level pixel of window cell (0, 0)
   int qxa[kMaxL], qya[kMaxL], qnx[kMaxL], qny[kMaxL];
   int qoff[kMaxL + 1];                        // prefix of the tile's query counts per level
+  uint32_t fill_bytes;                        // bytes the bulk copies of this tile's windows will deliver (in-level cells)
 };
 
 __device__ __forceinline__ int ceil_div_i(int a, int b) { return (a + b - 1) / b; }
@@ -133,7 +143,7 @@ __device__ inline void geom_init(Geom& g, const int64_t* __restrict__ shapes, co
 __device__ __forceinline__ void geom_tile(Geom& g, int tile, int lane) {
   const int ty = tile / g.tiles_x, tx = tile - ty * g.tiles_x;
   const int Wf = g.W[g.lf] > 0 ? g.W[g.lf] : 1, Hf = g.H[g.lf] > 0 ? g.H[g.lf] : 1;
-  int cnt = 0;
+  int cnt = 0, cells = 0;
   if (lane < g.L) {
     const int l = lane;
     g.wx0[l] = static_cast<int>(div_fast(2ll * kTW * tx * g.W[l] + Wf, 2ll * Wf)) - g.halo;
@@ -142,7 +152,14 @@ __device__ __forceinline__ void geom_tile(Geom& g, int tile, int lane) {
     const int ya = tile_first(ty, kTH, g.H[l], Hf), yb = tile_first(ty + 1, kTH, g.H[l], Hf);
     g.qxa[l] = xa; g.qya[l] = ya; g.qnx[l] = xb - xa; g.qny[l] = yb - ya;
     cnt = (xb - xa) * (yb - ya);
+    // window cells that lie inside the level: the ones fill_windows_bulk copies (the others are zero-filled)
+    const int x0 = max(g.wx0[l], 0), x1 = min(g.wx0[l] + g.wdx[l], g.W[l]);
+    const int y0 = max(g.wy0[l], 0), y1 = min(g.wy0[l] + g.wdy[l], g.H[l]);
+    cells = max(x1 - x0, 0) * max(y1 - y0, 0);
   }
+#pragma unroll
+  for (int sft = kMaxL / 2; sft >= 1; sft >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, sft);
+  if (lane == 0) g.fill_bytes = static_cast<uint32_t>(cells) * kRowBytes;
   int incl = cnt;
 #pragma unroll
   for (int sft = 1; sft < kMaxL; sft <<= 1) {
@@ -221,6 +238,68 @@ __device__ __forceinline__ void fill_windows(const Geom& g, uint32_t win, const 
         const bool in = yin && static_cast<unsigned>(gx) < static_cast<unsigned>(W);
         const uint32_t off = static_cast<uint32_t>(in ? gx : 0) * pixb;
         cp_async16_zfill(dst, srow + off, in);
+      }
+    }
+    task0 += wdy;
+  }
+}
+
+// ---- TMA bulk copies (descriptor-free: shapes stay on the device) + mbarrier completion ----------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MSDA_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MSDA_DONE;\n"
+      "bra MSDA_WAIT;\n"
+      "MSDA_DONE:\n"
+      "}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Window fill through the TMA unit: one 64-byte bulk copy (SASS UBLKCP) per window pixel that lies inside its level --
+// one lane per pixel, one warp per window row -- completing on `mbar`, whose expected byte count (g.fill_bytes, armed by
+// the caller) is exactly the bytes issued here; cells outside the level get plain zero stores (the zero padding).
+// ~17x fewer instructions than the 16-byte cp.async loop, and the copies do not pass through the LSU.
+template <typename T>
+__device__ __forceinline__ void fill_windows_bulk(const Geom& g, unsigned char* win_ptr, uint32_t win, uint32_t mbar,
+                                                  const T* __restrict__ value, int b, int S, int vps, int head, int warp,
+                                                  int lane, int nwarps) {
+  int task0 = 0;
+  const uint32_t pixb = static_cast<uint32_t>(vps) * static_cast<uint32_t>(sizeof(T));
+  const char* img = reinterpret_cast<const char*>(value) + static_cast<size_t>(b) * S * pixb + static_cast<size_t>(head) * kRowBytes;
+  for (int l = 0; l < g.L; ++l) {
+    const int wdx = g.wdx[l], wdy = g.wdy[l];
+    const int H = g.H[l], W = g.W[l], wx0 = g.wx0[l], wy0 = g.wy0[l];
+    const char* lvl = img + static_cast<size_t>(g.start[l]) * pixb;
+    int wy = warp - task0 % nwarps;
+    if (wy < 0) wy += nwarps;
+    for (; wy < wdy; wy += nwarps) {
+      const int gy = wy0 + wy;
+      const bool yin = static_cast<unsigned>(gy) < static_cast<unsigned>(H);
+      const uint32_t row = static_cast<uint32_t>(g.base[l] + wy * wdx);
+      const char* srow = lvl + static_cast<size_t>(static_cast<uint32_t>(yin ? gy : 0) * static_cast<uint32_t>(W)) * pixb;
+      for (int x = lane; x < wdx; x += 32) {
+        const int gx = wx0 + x;
+        if (yin && static_cast<unsigned>(gx) < static_cast<unsigned>(W)) {
+          bulk_copy_g2s(win + (row + x) * kRowBytes, srow + static_cast<uint32_t>(gx) * pixb, kRowBytes, mbar);
+        } else {
+          uint4* cell = reinterpret_cast<uint4*>(win_ptr + static_cast<size_t>(row + x) * kRowBytes);
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+          cell[0] = z; cell[1] = z; cell[2] = z; cell[3] = z;
+        }
       }
     }
     task0 += wdy;
@@ -324,7 +403,10 @@ msda_fwd_tiled_kernel(const T* __restrict__ value, const int64_t* __restrict__ s
   __shared__ Geom g;
   __shared__ int s_qid[2][kQC];
   __shared__ int s_ovf;
+  __shared__ __align__(8) unsigned long long s_mbar;       // completion of the window fill's bulk copies
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t mbar = smem_u32(&s_mbar);
+  uint32_t fill_parity = 0;
   SlotMap sm;
   sm.init(L, P, tid);
   const int LP = sm.LP, LP8 = sm.LP8;
@@ -333,7 +415,7 @@ msda_fwd_tiled_kernel(const T* __restrict__ value, const int64_t* __restrict__ s
   uint32_t* s_wts = s_rows + kChunkPts;              // [side][slot]
   const uint32_t win = smem_u32(win_ptr);
 
-  if (tid == 0) { geom_init(g, shapes, lsi, L, kWinRowsCap); s_ovf = 0; }
+  if (tid == 0) { geom_init(g, shapes, lsi, L, kWinRowsCap); s_ovf = 0; mbar_init(mbar, 1); }
   if (tid < 2 * kRowBytes / 16)                      // the zero rows: written once, never overwritten
     reinterpret_cast<uint4*>(win_ptr + static_cast<size_t>(kZeroRow) * kRowBytes)[tid] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
@@ -352,8 +434,14 @@ msda_fwd_tiled_kernel(const T* __restrict__ value, const int64_t* __restrict__ s
     __syncthreads();                                 // the previous work item no longer reads windows / geometry / qids
     if (warp == 0) geom_tile(g, tile, lane);
     __syncthreads();
-    fill_windows<T>(g, win, value, b, S, vps, head, warp, lane, kThreadsT / 32);
-    cp_async_commit();
+    if (kFillBulk) {
+      if (tid == 0) mbar_arrive_expect_tx(mbar, g.fill_bytes);
+      fence_proxy_async();               // earlier generic-proxy reads of the windows precede the async-proxy writes
+      fill_windows_bulk<T>(g, win_ptr, win, mbar, value, b, S, vps, head, warp, lane, kThreadsT / 32);
+    } else {
+      fill_windows<T>(g, win, value, b, S, vps, head, warp, lane, kThreadsT / 32);
+      cp_async_commit();
+    }
     const int nq = g.qoff[L];
     const T* img = value + static_cast<size_t>(b) * S * static_cast<size_t>(vps);
     if (tid < kQC) s_qid[0][tid] = tid < sm.qc ? tile_query(g, tid, Lq) : -1;
@@ -408,6 +496,7 @@ msda_fwd_tiled_kernel(const T* __restrict__ value, const int64_t* __restrict__ s
       if (more && tid < kQC) s_qid[buf ^ 1][tid] = tid < sm.qc ? tile_query(g, chunk0 + sm.qc + tid, Lq) : -1;
       cp_async_commit();
       cp_async_wait_all();
+      if (kFillBulk && chunk0 == 0) { mbar_wait(mbar, fill_parity); fill_parity ^= 1u; }
       __syncthreads();                               // records, windows, overflow rows and the next chunk's query ids are visible
       if (tid == 0) s_ovf = 0;                       // slots of this chunk are assigned; nobody touches the counter until the next phase A
       if (more) prefetch(s_qid[buf ^ 1]);            // in flight during the gather
@@ -492,7 +581,10 @@ msda_bwd_dots_tiled_kernel(const T* __restrict__ value, const int64_t* __restric
   __shared__ Geom g;
   __shared__ int s_qid[2][kQC];
   __shared__ int s_ovf;
+  __shared__ __align__(8) unsigned long long s_mbar;       // completion of the window fill's bulk copies
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t mbar = smem_u32(&s_mbar);
+  uint32_t fill_parity = 0;
   SlotMap sm;
   sm.init(L, P, tid);
   const int LP = sm.LP, LP8 = sm.LP8;
@@ -504,7 +596,7 @@ msda_bwd_dots_tiled_kernel(const T* __restrict__ value, const int64_t* __restric
   const uint32_t win = smem_u32(win_ptr);
   const uint32_t go_base = smem_u32(s_go);
 
-  if (tid == 0) { geom_init(g, shapes, lsi, L, kWinRowsCap); s_ovf = 0; }
+  if (tid == 0) { geom_init(g, shapes, lsi, L, kWinRowsCap); s_ovf = 0; mbar_init(mbar, 1); }
   if (tid < 2 * kRowBytes / 16)
     reinterpret_cast<uint4*>(win_ptr + static_cast<size_t>(kZeroRow) * kRowBytes)[tid] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
@@ -528,8 +620,14 @@ msda_bwd_dots_tiled_kernel(const T* __restrict__ value, const int64_t* __restric
     __syncthreads();
     if (warp == 0) geom_tile(g, tile, lane);
     __syncthreads();
-    fill_windows<T>(g, win, value, b, S, vps, head, warp, lane, kThreadsT / 32);
-    cp_async_commit();
+    if (kFillBulk) {
+      if (tid == 0) mbar_arrive_expect_tx(mbar, g.fill_bytes);
+      fence_proxy_async();               // earlier generic-proxy reads of the windows precede the async-proxy writes
+      fill_windows_bulk<T>(g, win_ptr, win, mbar, value, b, S, vps, head, warp, lane, kThreadsT / 32);
+    } else {
+      fill_windows<T>(g, win, value, b, S, vps, head, warp, lane, kThreadsT / 32);
+      cp_async_commit();
+    }
     const int nq = g.qoff[L];
     const T* img = value + static_cast<size_t>(b) * S * static_cast<size_t>(vps);
     if (tid < kQC) s_qid[0][tid] = tid < sm.qc ? tile_query(g, tid, Lq) : -1;
@@ -579,6 +677,7 @@ msda_bwd_dots_tiled_kernel(const T* __restrict__ value, const int64_t* __restric
       if (more && tid < kQC) s_qid[buf ^ 1][tid] = tid < sm.qc ? tile_query(g, chunk0 + sm.qc + tid, Lq) : -1;
       cp_async_commit();
       cp_async_wait_all();
+      if (kFillBulk && chunk0 == 0) { mbar_wait(mbar, fill_parity); fill_parity ^= 1u; }
       __syncthreads();
       if (tid == 0) s_ovf = 0;
       if (more) prefetch(s_qid[buf ^ 1]);
