@@ -189,6 +189,47 @@ def test_stacked_views_match_dense_copies(ops, dtype, Lq):
     assert torch.isfinite(grad_all).all()
 
 
+@pytest.mark.parametrize("flags", [0, 2])      # cluster guard raising its flag / fp32 accumulation asked for
+def test_stacked_views_with_fp32_accumulation(ops, flags):
+    """Strided grad_value with the fp32-accumulation pipeline (round 2: the rounding pass writes strided rows): reached
+    through the cluster guard on a crowded call, or explicitly with MSDA_BWD_GRAD_VALUE_FP32_ACCUM."""
+    from vision_instance_seg_b200 import MultiScaleDeformableAttention as MSDA
+    from vision_instance_seg_b200 import _lib
+    lib = _lib.load_library()
+    dev = "cuda:0"
+    K, N, M, D, P, Lq = 3, 2, 8, 32, 4, 200
+    shapes = [(16, 16), (8, 8), (4, 4)]
+    g = torch.Generator().manual_seed(14)
+    ss = torch.as_tensor(shapes, dtype=torch.long)
+    S, L = int(ss.prod(1).sum()), 3
+    value_all = torch.randn(N, S, K, M, D, generator=g).to(dev, torch.bfloat16)
+    loc = (0.5 + 0.004 * torch.randn(N, Lq, M, L, P, 2, generator=g)).to(dev)          # every point on the same few pixels
+    attn = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P).to(dev)
+    go = (torch.randn(N, Lq, M * D, generator=g) + 1.0).to(dev, torch.bfloat16)
+    ssd, lsid = ss.to(dev), lsi_of(ss).to(dev)
+    layer = 1
+    grad_all = torch.full_like(value_all, float("nan"))
+    stride = K * M * D
+    off = layer * M * D * 2
+    nbytes = lib.msda_backward_scratch_bytes(N, S, M, D, Lq, L, P, _lib.MSDA_BF16, flags)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    gl, ga = torch.empty_like(loc), torch.empty_like(attn)
+    rc = lib.msda_backward_strided(value_all.data_ptr() + off, stride, ssd.data_ptr(), lsid.data_ptr(), loc.data_ptr(),
+                                   attn.data_ptr(), go.data_ptr(), grad_all.data_ptr() + off, stride, gl.data_ptr(),
+                                   ga.data_ptr(), scratch.data_ptr(), nbytes, N, S, M, D, Lq, L, P, _lib.MSDA_BF16, 64, flags,
+                                   torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    if flags == 0:
+        assert int(scratch[:8].view(torch.int32)[1]) == 1, "the crowded call should have raised the cluster flag"
+    dense = value_all[:, :, layer].contiguous()
+    want = oracle_on_rounded_inputs(dense.float().cpu(), ss, loc.cpu(), attn.cpu(), go.float().cpu(), torch.bfloat16)
+    assert rel_to_max(grad_all[:, :, layer], want[1]) < 5e-3
+    assert rel_to_max(gl, want[2]) < 2e-2 and rel_to_max(ga, want[3]) < 2e-2
+    for other in (0, 2):
+        assert torch.isnan(grad_all[:, :, other]).all(), "strided backward wrote outside its layer"
+
+
 def test_strided_entry_points_validate_strides(ops):
     import ctypes
     from vision_instance_seg_b200 import _lib
