@@ -769,17 +769,20 @@ msda_bwd_dots_tiled_kernel(const T* __restrict__ value, const int64_t* __restric
 // Backward, part 2: grad_value by counting sort + segmented sums (no read-modify-write in shared memory)
 // =====================================================================================================
 constexpr int kScThreads = 256;
-constexpr int kScIters = 3;                       // points per thread per level round
-constexpr int kScPoints = kScThreads * kScIters;  // points of one level handled per round
-constexpr int kScEntries = kScPoints * 4;         // corner rows per round
-constexpr int kScQueries = 256;                   // queries per round (8-bit local index)
+constexpr int kScLG = 2;                          // levels sorted together per round
+constexpr int kScIters = 6;                       // point slots per thread per round
+constexpr int kScPoints = kScThreads * kScIters;  // point slots per round
+constexpr int kScEntries = 2 * kScPoints;         // pair entries per round (top and bottom row of every point)
+constexpr int kScQueries = 192;                   // queries per round (8-bit local index)
 constexpr int kScMaxRun = 64;                     // adds per fp16 register accumulator before it is flushed
+constexpr int kScClasses = 64;                    // bins are ordered by min(count, 63)
 
 // shared memory: go2 [kScQueries][2][64 B] | entries [kScEntries] uint2 | cnt [kWinRowsCap + 1] u32 | dst [kWinRowsCap] u32 |
-//                qid [kScQueries]
+//                order [kWinRowsCap] u16 | qid [kScQueries] | hist [kScClasses] | hist_start [kScClasses]
 constexpr size_t kScSmemBytes = static_cast<size_t>(kScQueries) * 2 * kRowBytes + static_cast<size_t>(kScEntries) * 8 +
                                 static_cast<size_t>(kWinRowsCap + 1) * 4 + static_cast<size_t>(kWinRowsCap) * 4 +
-                                static_cast<size_t>(kScQueries) * 4;
+                                static_cast<size_t>(kWinRowsCap) * 2 + static_cast<size_t>(kScQueries) * 4 +
+                                static_cast<size_t>(kScClasses) * 8;
 
 __device__ __forceinline__ uint32_t hfma2_u32(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t d;
@@ -787,10 +790,47 @@ __device__ __forceinline__ uint32_t hfma2_u32(uint32_t a, uint32_t b, uint32_t c
   return d;
 }
 
-// The accumulation runs in the representation of the global accumulator itself: grad_out is staged as fp16 already
-// multiplied by the accumulator's power-of-two scale (f16_accum_scale: no sum of |weight * grad_out| over a whole image
-// can overflow), weights are fp16, a lane sums at most kScMaxRun products per register pair (HFMA2) and then issues one
-// packed fp16 reduction -- no unpack, scale or pack in the loop or in the flush.
+// per-level constants of the count phase
+struct ScLevel {
+  int l, H, W, wx0, wy0, wdx, wdy, lbase;
+  uint32_t acc_row0;
+  float Hf, Wf;
+};
+__device__ __forceinline__ ScLevel sc_level(const Geom& g, const LevelMeta& meta, int l0, int lv, int tile) {
+  ScLevel s;
+  s.l = l0 + lv;
+  s.H = g.H[s.l]; s.W = g.W[s.l];
+  s.Hf = static_cast<float>(s.H); s.Wf = static_cast<float>(s.W);
+  s.wx0 = g.wx0[s.l]; s.wy0 = g.wy0[s.l]; s.wdx = g.wdx[s.l]; s.wdy = g.wdy[s.l];
+  s.lbase = 0;
+  for (int k = 0; k < lv; ++k) s.lbase += g.wdx[l0 + k] * g.wdy[l0 + k];
+  const int K = meta.accK[s.l];
+  s.acc_row0 = static_cast<uint32_t>(meta.accBase[s.l]) + static_cast<uint32_t>(K > 1 ? tile % K : 0) * static_cast<uint32_t>(s.H * s.W);
+  return s;
+}
+// a footprint row that leaves its window: both 64-byte rows straight into the accumulator (rare)
+static __device__ __noinline__ void sc_slow_pair(__half* dst, size_t pix_elems, const unsigned char* go_row, uint32_t wbits, bool do_l, bool do_r) {
+  const uint32_t wl2 = __byte_perm(wbits, 0, 0x1010), wr2 = __byte_perm(wbits, 0, 0x3232);
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    const uint4 u = *reinterpret_cast<const uint4*>(go_row + ch * 16);
+    if (do_l)
+      red_add_16bit_x8<__half>(dst + ch * 8, make_uint4(hfma2_u32(wl2, u.x, 0u), hfma2_u32(wl2, u.y, 0u),
+                                                       hfma2_u32(wl2, u.z, 0u), hfma2_u32(wl2, u.w, 0u)));
+    if (do_r)
+      red_add_16bit_x8<__half>(dst + pix_elems + ch * 8, make_uint4(hfma2_u32(wr2, u.x, 0u), hfma2_u32(wr2, u.y, 0u),
+                                                                   hfma2_u32(wr2, u.z, 0u), hfma2_u32(wr2, u.w, 0u)));
+  }
+}
+
+// Unit of the sort: an x-adjacent corner PAIR (left pixel x0, right pixel x0 + 1 of one footprint row) -- both corners
+// scale the same grad_out row, so a pair entry (bin = window cell of the left pixel, local query, two fp16 weights) halves
+// the ranks, the places and the grad_out row reads of a per-corner sort.  Two levels are sorted together per round.
+// After the exclusive scan the non-empty bins are ordered by their entry count (a second, 64-class counting sort), and
+// the 4-lane groups take bins in that order: the 8 groups of a warp then work on bins of (nearly) equal length, every
+// group sums its bin's left and right pixel in fp16 registers (HFMA2; grad_out staged as fp16 already multiplied by
+// the accumulator's power-of-two scale, at both 64-byte parities) and the whole warp reaches the flush -- two packed fp16
+// reductions per bin -- together.  A register accumulator takes at most kScMaxRun products between flushes.
 template <typename T>
 __global__ void __launch_bounds__(kScThreads, 3)
 msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
@@ -801,13 +841,16 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
   __shared__ Geom g;
   __shared__ LevelMeta meta;
   __shared__ uint32_t s_warp_tot[kScThreads / 32];
-  __shared__ uint32_t s_total;
+  __shared__ uint32_t s_total, s_nbins;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned char* s_go = smem_raw;
   uint2* s_ent = reinterpret_cast<uint2*>(smem_raw + static_cast<size_t>(kScQueries) * 2 * kRowBytes);
   uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_ent + kScEntries);
   uint32_t* s_dst = s_cnt + kWinRowsCap + 1;
-  int* s_qid = reinterpret_cast<int*>(s_dst + kWinRowsCap);
+  uint16_t* s_order = reinterpret_cast<uint16_t*>(s_dst + kWinRowsCap);
+  int* s_qid = reinterpret_cast<int*>(s_order + kWinRowsCap);
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_qid + kScQueries);
+  uint32_t* s_hstart = s_hist + kScClasses;
   const uint32_t go_base = smem_u32(s_go);
 
   load_level_meta(meta, shapes, lsi, L);
@@ -817,8 +860,8 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
   const float gv_scale = f16_accum_scale(ctrl, Lq);
   const int tiles = g.tiles_x * g.tiles_y;
   const long long total = static_cast<long long>(N) * tiles * M;
-  const int q_round = min(kScQueries, kScPoints / P);       // P <= kMaxLP <= kScPoints
-  const int grp = tid >> 2, c = tid & 3;                    // 4-lane group: one sorted range; lane = 8 channels
+  const int q_round = max(1, min(kScQueries, kScPoints / (P * kScLG)));
+  const int grp = tid >> 2, c = tid & 3;                    // 4-lane group: one bin at a time; lane = 8 channels
   const uint32_t go_lane = static_cast<uint32_t>(((grp & 1) * kRowBytes) + c * 16);   // copy of the row in "my" half of the banks
   const size_t pix_elems = static_cast<size_t>(M) * kD;
   const int LP = L * P;
@@ -836,7 +879,6 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
 
     for (int q0 = 0; q0 < nq; q0 += q_round) {
       const int nqr = min(q_round, nq - q0);
-      const int npts = nqr * P;
       __syncthreads();                      // previous round no longer reads go rows / query ids
       for (int i = tid; i < nqr; i += kScThreads) s_qid[i] = tile_query(g, q0 + i, Lq);
       __syncthreads();
@@ -857,87 +899,80 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
         *reinterpret_cast<uint4*>(s_go + static_cast<size_t>(qi) * 2 * kRowBytes + ch * 16) = u;
         *reinterpret_cast<uint4*>(s_go + static_cast<size_t>(qi) * 2 * kRowBytes + kRowBytes + ch * 16) = u;
       }
-      // sampling locations / weights of one level's points: thread = point (slot tid + it * kScThreads)
-      float2 pxy[kScIters];
-      float pa[kScIters];
-      auto prefetch = [&](int l) {
-#pragma unroll
-        for (int it = 0; it < kScIters; ++it) {
-          const int idx = tid + it * kScThreads;
-          pxy[it] = make_float2(nanf_, nanf_);
-          pa[it] = 0.f;
-          if (idx < npts) {
-            const int qi = static_cast<int>(static_cast<uint32_t>(idx) / static_cast<uint32_t>(P)), p = idx - qi * P;
-            const int q = s_qid[qi];
-            if (q >= 0) {
-              const size_t pair = (static_cast<size_t>(b) * Lq + q) * M + head;
-              pxy[it] = __ldg(reinterpret_cast<const float2*>(loc) + pair * LP + l * P + p);
-              pa[it] = __ldg(attn + pair * LP + l * P + p);
-            }
-          }
-        }
-      };
-      prefetch(0);
 
-      for (int l = 0; l < L; ++l) {
-        const int H = g.H[l], W = g.W[l];
-        const float Hf = static_cast<float>(H), Wf = static_cast<float>(W);
-        const int wdx = g.wdx[l], wdy = g.wdy[l], nrows = wdx * wdy;
-        const int wx0 = g.wx0[l], wy0 = g.wy0[l];
-        const int K = meta.accK[l];
-        const size_t acc_row0 = static_cast<size_t>(meta.accBase[l]) + static_cast<size_t>(K > 1 ? tile % K : 0) * (static_cast<size_t>(H) * W);
-        __syncthreads();                    // previous level's entries / counters are no longer read; go rows are staged
+      for (int l0 = 0; l0 < L; l0 += kScLG) {
+        const int lg = min(kScLG, L - l0);                  // levels of this round
+        const int ppq = P * lg;                             // point slots per query
+        const int npts = nqr * ppq;
+        // first window row (bin) of every level of the round, and the round's bin count
+        int nrows = 0;
+        for (int lv = 0; lv < lg; ++lv) nrows += g.wdx[l0 + lv] * g.wdy[l0 + lv];
+        __syncthreads();                    // previous round's entries / counters / order are no longer read; go rows are staged
         for (int i = tid; i <= nrows; i += kScThreads) s_cnt[i] = 0u;
+        if (tid < kScClasses) s_hist[tid] = 0u;
         __syncthreads();
-        // ---- count: every valid corner inside the window takes a rank in its destination row's bin ----
-        uint32_t keyrank[kScIters][4];      // key | rank << 16; 0xFFFFFFFF = no entry
-        uint32_t payload[kScIters][4];      // fp16 weight, twice
+        // ---- count: thread = point slot; each footprint row inside the window takes a rank in its pair bin ----
+        uint32_t keyrank[kScIters][2];      // key | rank << 16; 0xFFFFFFFF = no entry
+        uint32_t payload[kScIters][2];      // fp16 weight of the left | right pixel
+        uint32_t qis[kScIters];
+        // slot = qi * ppq + lv * P + p.  When ppq divides the CTA size a thread's (lv, p) never changes: decode once and
+        // keep the level's constants in registers
+        const bool fixed = (kScThreads % ppq) == 0;
+        const int remF = tid % ppq, qiF = tid / ppq, qstep = kScThreads / ppq;
+        ScLevel sl = sc_level(g, meta, l0, static_cast<int>(static_cast<uint32_t>(remF) / static_cast<uint32_t>(P)), tile);
+        const int pF = remF - (remF / P) * P;
 #pragma unroll
         for (int it = 0; it < kScIters; ++it) {
+          keyrank[it][0] = keyrank[it][1] = 0xFFFFFFFFu;
+          qis[it] = 0u;
+          int qi, p;
+          if (fixed) {
+            qi = qiF + it * qstep; p = pF;
+          } else {
+            const int slot = tid + it * kScThreads;
+            qi = static_cast<int>(static_cast<uint32_t>(slot) / static_cast<uint32_t>(ppq));
+            const int rem = slot - qi * ppq;
+            const int lv = static_cast<int>(static_cast<uint32_t>(rem) / static_cast<uint32_t>(P));
+            p = rem - lv * P;
+            sl = sc_level(g, meta, l0, lv, tile);
+          }
+          if (qi >= nqr) continue;
+          const int q = s_qid[qi];
+          if (q < 0) continue;
+          qis[it] = static_cast<uint32_t>(qi);
+          const size_t pair = (static_cast<size_t>(b) * Lq + q) * M + head;
+          const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + pair * LP + sl.l * P + p);
+          const float a = __ldg(attn + pair * LP + sl.l * P + p);
+          const PointGeo pg = point_geo(xy.x, xy.y, sl.Hf, sl.Wf);
+          if (!pg.inside) continue;
+          const int wxr = pg.ix - sl.wx0, wyr0 = pg.iy - sl.wy0;
+          const bool lin = static_cast<unsigned>(pg.ix) < static_cast<unsigned>(sl.W);
+          const bool rin = static_cast<unsigned>(pg.ix + 1) < static_cast<unsigned>(sl.W);
+          const float wx_l = lin ? (1.f - pg.lw) : 0.f, wx_r = rin ? pg.lw : 0.f;
+          const float wy[2] = {(1.f - pg.lh) * a, pg.lh * a};
 #pragma unroll
-          for (int k = 0; k < 4; ++k) keyrank[it][k] = 0xFFFFFFFFu;
-          const PointGeo pg = point_geo(pxy[it].x, pxy[it].y, Hf, Wf);
-          if (pg.inside) {
-            const float ah = (1.f - pg.lh) * pa[it], al = pg.lh * pa[it];
-            const float hw = 1.f - pg.lw;
-            const float w[4] = {ah * hw, ah * pg.lw, al * hw, al * pg.lw};
-            const int wxr0 = pg.ix - wx0, wyr0 = pg.iy - wy0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int x = pg.ix + (k & 1), y = pg.iy + (k >> 1);
-              if (static_cast<unsigned>(x) >= static_cast<unsigned>(W) || static_cast<unsigned>(y) >= static_cast<unsigned>(H) || w[k] == 0.f)
-                continue;                                                        // zero padding / nothing to add
-              const int wxr = wxr0 + (k & 1), wyr = wyr0 + (k >> 1);
-              const __half2 w2 = __float2half2_rn(w[k]);
-              if (static_cast<unsigned>(wxr) < static_cast<unsigned>(wdx) && static_cast<unsigned>(wyr) < static_cast<unsigned>(wdy)) {
-                const uint32_t key = static_cast<uint32_t>(wyr * wdx + wxr);
-                const uint32_t rank = atomicAdd(&s_cnt[key], 1u);
-                keyrank[it][k] = key | (rank << 16);
-                payload[it][k] = *reinterpret_cast<const uint32_t*>(&w2);
-              } else {
-                // slow path: the whole 64-byte row of this corner, reduced straight into the accumulator
-                const int qi = static_cast<int>(static_cast<uint32_t>(tid + it * kScThreads) / static_cast<uint32_t>(P));
-                __half* dst = acc_img - c * 8 + (acc_row0 + static_cast<size_t>(y) * W + x) * pix_elems;
-                const uint32_t wbits = *reinterpret_cast<const uint32_t*>(&w2);
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                  const uint4 u = *reinterpret_cast<const uint4*>(s_go + static_cast<size_t>(qi) * 2 * kRowBytes + ch * 16);
-                  uint4 r;
-                  r.x = hfma2_u32(wbits, u.x, 0u); r.y = hfma2_u32(wbits, u.y, 0u);
-                  r.z = hfma2_u32(wbits, u.z, 0u); r.w = hfma2_u32(wbits, u.w, 0u);
-                  red_add_16bit_x8<__half>(dst + ch * 8, r);
-                }
-              }
+          for (int r = 0; r < 2; ++r) {
+            const int y = pg.iy + r;
+            if (static_cast<unsigned>(y) >= static_cast<unsigned>(sl.H)) continue;       // zero padding
+            const float wl = wy[r] * wx_l, wr = wy[r] * wx_r;
+            if (wl == 0.f && wr == 0.f) continue;
+            const __half2 w2 = __floats2half2_rn(wl, wr);
+            const uint32_t wbits = *reinterpret_cast<const uint32_t*>(&w2);
+            const int wyr = wyr0 + r;
+            if (wxr >= 0 && wxr <= sl.wdx - 2 && static_cast<unsigned>(wyr) < static_cast<unsigned>(sl.wdy)) {
+              const uint32_t key = static_cast<uint32_t>(sl.lbase + wyr * sl.wdx + wxr);
+              const uint32_t rank = atomicAdd(&s_cnt[key], 1u);
+              keyrank[it][r] = key | (rank << 16);
+              payload[it][r] = wbits;
+            } else {
+              // slow path: the two 64-byte rows of this pair, reduced straight into the accumulator
+              sc_slow_pair(acc_img - c * 8 + (static_cast<size_t>(sl.acc_row0) + static_cast<size_t>(y) * sl.W + pg.ix) * pix_elems,
+                           pix_elems, s_go + static_cast<size_t>(qi) * 2 * kRowBytes, wbits, lin && wl != 0.f, rin && wr != 0.f);
             }
           }
         }
-        int qi_of[kScIters];
-#pragma unroll
-        for (int it = 0; it < kScIters; ++it)
-          qi_of[it] = static_cast<int>(static_cast<uint32_t>(tid + it * kScThreads) / static_cast<uint32_t>(P));
-        if (l + 1 < L) prefetch(l + 1);     // in flight during scan / place / sums
         __syncthreads();
-        // ---- exclusive scan of the bin counts (in place) + destination pixel of every bin ----
+        // ---- exclusive scan of the bin counts (in place), destination of every bin, histogram of the bin lengths ----
         {
           const int per = (nrows + kScThreads - 1) / kScThreads;       // <= 6
           const int r0 = tid * per, r1 = min(nrows, r0 + per);
@@ -955,55 +990,98 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
           for (int w2 = 0; w2 < warp; ++w2) woff += s_warp_tot[w2];
           uint32_t run = woff + incl - sum;
           if (r0 < r1) {
-            int wyr = static_cast<int>(static_cast<uint32_t>(r0) / static_cast<uint32_t>(wdx)), wxr = r0 - wyr * wdx;
+            // (level, window cell) of bin r0, then walk
+            int lv = 0, rr = r0;
+            while (lv + 1 < lg && rr >= g.wdx[l0 + lv] * g.wdy[l0 + lv]) { rr -= g.wdx[l0 + lv] * g.wdy[l0 + lv]; ++lv; }
+            int l = l0 + lv;
+            int wdx = g.wdx[l];
+            int wyr = static_cast<int>(static_cast<uint32_t>(rr) / static_cast<uint32_t>(wdx)), wxr = rr - wyr * wdx;
             for (int r = r0; r < r1; ++r) {
               const uint32_t cnt = s_cnt[r];
               s_cnt[r] = run;
               run += cnt;
-              s_dst[r] = static_cast<uint32_t>((wy0 + wyr) * W + (wx0 + wxr));   // only read for bins that hold entries
-              if (++wxr == wdx) { wxr = 0; ++wyr; }
+              if (cnt != 0u) {
+                const int H = g.H[l], W = g.W[l];
+                const int K = meta.accK[l];
+                const uint32_t acc_row0 = static_cast<uint32_t>(meta.accBase[l]) + static_cast<uint32_t>(K > 1 ? tile % K : 0) * static_cast<uint32_t>(H * W);
+                const int x = g.wx0[l] + wxr, y = g.wy0[l] + wyr;
+                const uint32_t lbit = static_cast<unsigned>(x) < static_cast<unsigned>(W) ? 0x80000000u : 0u;
+                const uint32_t rbit = static_cast<unsigned>(x + 1) < static_cast<unsigned>(W) ? 0x40000000u : 0u;
+                // row of the left pixel, or of the right one when the left lies outside the level (x == -1)
+                s_dst[r] = ((acc_row0 + static_cast<uint32_t>(y * W + (lbit ? x : x + 1))) & 0x3FFFFFFFu) | lbit | rbit;
+                atomicAdd(&s_hist[min(cnt, static_cast<uint32_t>(kScClasses - 1))], 1u);
+              }
+              if (++wxr == wdx) {
+                wxr = 0;
+                if (++wyr == g.wdy[l]) { wyr = 0; ++lv; l = l0 + (lv < lg ? lv : lg - 1); wdx = g.wdx[l]; }
+              }
             }
           }
-          if (tid == kScThreads - 1) s_total = woff + incl;
+          if (tid == kScThreads - 1) { s_total = woff + incl; s_cnt[nrows] = woff + incl; }
         }
         __syncthreads();
-        // ---- place the entries ----
+        // ---- order of the non-empty bins: longest first (descending 64-class counting sort) ----
+        if (warp == 0) {
+          const uint32_t ha = s_hist[kScClasses - 1 - 2 * lane], hb = s_hist[kScClasses - 2 - 2 * lane];
+          uint32_t incl = ha + hb;
+#pragma unroll
+          for (int sft = 1; sft < 32; sft <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, sft);
+            if (lane >= sft) incl += t;
+          }
+          const uint32_t excl = incl - (ha + hb);
+          s_hstart[kScClasses - 1 - 2 * lane] = excl;
+          s_hstart[kScClasses - 2 - 2 * lane] = excl + ha;
+          s_hist[kScClasses - 1 - 2 * lane] = 0u;       // reused as fill counters
+          s_hist[kScClasses - 2 - 2 * lane] = 0u;
+          if (lane == 31) s_nbins = incl;
+        }
+        __syncthreads();
+        // ---- place the entries and the bins ----
 #pragma unroll
         for (int it = 0; it < kScIters; ++it) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t kr = keyrank[it][k];
+          for (int r = 0; r < 2; ++r) {
+            const uint32_t kr = keyrank[it][r];
             if (kr != 0xFFFFFFFFu) {
               const uint32_t key = kr & 0xFFFFu;
-              s_ent[s_cnt[key] + (kr >> 16)] = make_uint2(key | (static_cast<uint32_t>(qi_of[it]) << 16), payload[it][k]);
+              s_ent[s_cnt[key] + (kr >> 16)] = make_uint2(key | (qis[it] << 16), payload[it][r]);
             }
           }
         }
-        __syncthreads();
-        // ---- segmented sums: every 4-lane group walks a contiguous range of the sorted list ----
-        {
-          const int E = static_cast<int>(s_total);
-          const int ngroups = kScThreads / 4;
-          const int per = (E + ngroups - 1) / ngroups;
-          const int e0 = grp * per, e1 = min(E, e0 + per);
-          uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-          uint32_t cur = 0xFFFFFFFFu;
-          int e_flush = e0 + kScMaxRun;
-          __half* acc_lvl = acc_img + acc_row0 * pix_elems;
-          for (int e = e0; e < e1; ++e) {
-            const uint2 ent = s_ent[e];
-            const uint32_t key = ent.x & 0xFFFFu;
-            if (key != cur || e == e_flush) {
-              if (cur != 0xFFFFFFFFu) red_add_16bit_x8<__half>(acc_lvl + static_cast<size_t>(s_dst[cur]) * pix_elems, acc);
-              acc = make_uint4(0u, 0u, 0u, 0u);
-              cur = key;
-              e_flush = e + kScMaxRun;
-            }
-            const uint4 u = lds128(go_base + (ent.x >> 16) * (2 * kRowBytes) + go_lane);
-            acc.x = hfma2_u32(ent.y, u.x, acc.x); acc.y = hfma2_u32(ent.y, u.y, acc.y);
-            acc.z = hfma2_u32(ent.y, u.z, acc.z); acc.w = hfma2_u32(ent.y, u.w, acc.w);
+        for (int r = tid; r < nrows; r += kScThreads) {
+          const uint32_t cnt = s_cnt[r + 1] - s_cnt[r];
+          if (cnt != 0u) {
+            const uint32_t cls = min(cnt, static_cast<uint32_t>(kScClasses - 1));
+            s_order[s_hstart[cls] + atomicAdd(&s_hist[cls], 1u)] = static_cast<uint16_t>(r);
           }
-          if (cur != 0xFFFFFFFFu) red_add_16bit_x8<__half>(acc_lvl + static_cast<size_t>(s_dst[cur]) * pix_elems, acc);
+        }
+        __syncthreads();
+        // ---- sums: one bin per 4-lane group at a time, bins in order of decreasing length ----
+        {
+          const int nbins = static_cast<int>(s_nbins);
+          const int ngroups = kScThreads / 4;
+          for (int i = grp; i < nbins; i += ngroups) {
+            const uint32_t r = s_order[i];
+            const uint32_t e0 = s_cnt[r], e1 = s_cnt[r + 1];
+            const uint32_t dst = s_dst[r];
+            __half* row = acc_img + static_cast<size_t>(dst & 0x3FFFFFFFu) * pix_elems;
+            for (uint32_t ea = e0; ea < e1; ea += kScMaxRun) {
+              const uint32_t eb = min(e1, ea + static_cast<uint32_t>(kScMaxRun));
+              uint4 aL = make_uint4(0u, 0u, 0u, 0u), aR = aL;
+              for (uint32_t e = ea; e < eb; ++e) {
+                const uint2 ent = s_ent[e];
+                const uint4 u = lds128(go_base + (ent.x >> 16) * (2 * kRowBytes) + go_lane);
+                const uint32_t wl2 = __byte_perm(ent.y, 0, 0x1010), wr2 = __byte_perm(ent.y, 0, 0x3232);
+                aL.x = hfma2_u32(wl2, u.x, aL.x); aL.y = hfma2_u32(wl2, u.y, aL.y);
+                aL.z = hfma2_u32(wl2, u.z, aL.z); aL.w = hfma2_u32(wl2, u.w, aL.w);
+                aR.x = hfma2_u32(wr2, u.x, aR.x); aR.y = hfma2_u32(wr2, u.y, aR.y);
+                aR.z = hfma2_u32(wr2, u.z, aR.z); aR.w = hfma2_u32(wr2, u.w, aR.w);
+              }
+              if (dst & 0x80000000u) red_add_16bit_x8<__half>(row, aL);
+              if (dst & 0x40000000u) red_add_16bit_x8<__half>((dst & 0x80000000u) ? row + pix_elems : row, aR);
+            }
+          }
         }
       }
     }
