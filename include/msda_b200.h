@@ -161,6 +161,16 @@ int msda_backward_strided(const void* value, long long value_pixel_stride,
  */
 int msda_set_tiled_mode(int mode);
 
+/*
+ * Mode 2 of msda_set_tiled_mode (MSDA_B200_TILED=2): hybrid backward for the same call site, forward unchanged.  The
+ * direct backward kernel computes grad_sampling_loc / grad_attn_weight and the grad_value reductions of the fine levels;
+ * the coarse levels -- those that expect more than `adds` corner rows per pixel row, ceil(Lq*P / (H_l*W_l)) > adds,
+ * where pre-reducing inside the SM removes most of the reductions the L2 would otherwise resolve -- get their
+ * grad_value from the sorting kernel of the tiled backward.  msda_set_hybrid_split sets `adds` (default 8; 0 switches
+ * the hybrid path off) and returns the previous value.
+ */
+int msda_set_hybrid_split(int adds);
+
 /* Number of kernel launches (not memsets) the last forward/backward call on this thread enqueued;
  * used by bench.py to report `gpu_launches`. */
 int msda_last_launch_count(void);

@@ -118,3 +118,44 @@ def test_tiled_mode_leaves_other_call_sites_alone(tiled_mode):
     n_off = lib.msda_last_launch_count()
     b200.set_tiled_mode(True)
     assert n_on == n_off == 1
+
+
+HYBRID_CASES = [c for c in CASES if c[0] in ("pyramid_bf16", "pyramid_f16", "pyramid_uniform", "pyramid_big_offsets", "odd_shapes",
+                                             "non_nested", "points3", "cfg3_one_image")]
+
+
+@pytest.mark.parametrize("split", [1, 8, 30])
+@pytest.mark.parametrize("name,shapes,batch,dtype,kind,kw", HYBRID_CASES, ids=[c[0] for c in HYBRID_CASES])
+def test_hybrid_backward_matches_oracle(name, shapes, batch, dtype, kind, kw, split):
+    """Mode 2 (msda_set_tiled_mode(2)): the direct backward kernel keeps grad_sampling_loc / grad_attn_weight and the
+    grad_value reductions of the levels that expect at most `split` corner rows per pixel row; the sorting kernel of the
+    tiled backward produces grad_value of the coarser levels.  split = 1: every level is sorted; 8: the finest level of
+    a /8../64 pyramid stays direct; 30: the two finest.  Same oracle, same 2e-2 gate (max-abs-error / max-abs-reference);
+    the aux gradients come from the direct kernel unchanged, so they must be bit-identical to mode 0."""
+    import vision_instance_seg_b200 as b200
+    from vision_instance_seg_b200 import MultiScaleDeformableAttention as MSDA
+    from vision_instance_seg_b200 import workloads
+    dev = "cuda"
+    make = workloads.make_encoder_inputs if kind == "encoder" else workloads.make_uniform_inputs
+    if kind != "encoder":
+        kw = {k: v for k, v in kw.items() if k != "offset_sigma_px"}
+    value, ss, lsi, loc, attn = make(shapes, batch, dtype, seed=13, device=dev, **kw)
+    g = torch.Generator(device=dev).manual_seed(6)
+    go = torch.randn(batch, loc.shape[1], value.shape[2] * 32, generator=g, device=dev).to(dtype)
+    prev_mode, prev_split = b200.set_tiled_mode(2), b200.set_hybrid_split(split)
+    try:
+        lib = b200.load_library()
+        hyb = MSDA.ms_deform_attn_backward(value, ss, lsi, loc, attn, go, 128)
+        launches = lib.msda_last_launch_count()
+        torch.cuda.synchronize()
+        b200.set_tiled_mode(0)
+        direct = MSDA.ms_deform_attn_backward(value, ss, lsi, loc, attn, go, 128)
+        torch.cuda.synchronize()
+    finally:
+        b200.set_tiled_mode(prev_mode)
+        b200.set_hybrid_split(prev_split)
+    assert launches == 5, "zero, max|grad_out|, direct kernel, sorting kernel, rounding pass"
+    ref = ms_deform_attn_oracle_grads(value.float().cpu(), ss.cpu(), loc.cpu(), attn.cpu(), go.float().cpu())
+    assert rel_to_max(hyb[0].float().cpu(), ref[1].float()) < 2e-2, f"{name} split {split}: grad_value"
+    assert torch.equal(hyb[1], direct[1]) and torch.equal(hyb[2], direct[2])
+    assert rel_to_max(hyb[0], direct[0]) < 2e-2

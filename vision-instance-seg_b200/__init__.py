@@ -24,10 +24,17 @@ from .modules import (MSDeformAttn, set_fused_encoder_layers, set_fused_preop, s
 
 
 
-def set_tiled_mode(enabled: bool) -> bool:
-    """Switch the opt-in tiled kernels of the dense call site (Lq == S, 16-bit values, head dim 32; see
-    include/msda_b200.h ``msda_set_tiled_mode``) on or off for this process; returns the previous setting."""
-    return bool(load_library().msda_set_tiled_mode(1 if enabled else 0))
+def set_tiled_mode(mode) -> int:
+    """Select the kernels of the dense call site (Lq == S, 16-bit values, head dim 32; see include/msda_b200.h
+    ``msda_set_tiled_mode``) for this process: 0 / False = direct kernels, 1 / True = tiled forward and backward,
+    2 = hybrid backward (direct kernel + sorting kernel for the coarse levels).  Returns the previous mode."""
+    return int(load_library().msda_set_tiled_mode(int(mode)))
+
+
+def set_hybrid_split(adds: int) -> int:
+    """Levels that expect more than ``adds`` corner rows per pixel row go to the sorting kernel in mode 2 (see
+    include/msda_b200.h ``msda_set_hybrid_split``); returns the previous value."""
+    return int(load_library().msda_set_hybrid_split(int(adds)))
 
 
 def install_as_upstream_extension(name: str = "MultiScaleDeformableAttention"):
@@ -48,4 +55,4 @@ def install_as_upstream_extension(name: str = "MultiScaleDeformableAttention"):
 
 
 __all__ = ["MSDeformAttn", "MSDeformAttnFunction", "MSDeformAttnFusedFunction", "MultiScaleDeformableAttention",
-           "set_fused_preop", "set_fused_encoder_layers", "share_value_proj", "unshare_value_proj", "install_as_upstream_extension", "load_library", "library_path", "set_tiled_mode"]
+           "set_fused_preop", "set_fused_encoder_layers", "share_value_proj", "unshare_value_proj", "install_as_upstream_extension", "load_library", "library_path", "set_tiled_mode", "set_hybrid_split"]

@@ -36,6 +36,7 @@ EXPORTED_SYMBOLS = (
     "msda_forward_strided",
     "msda_backward_strided",
     "msda_set_tiled_mode",
+    "msda_set_hybrid_split",
     "msda_last_launch_count",
     "msda_total_launch_count",
     "msda_profile_enable",
@@ -66,6 +67,8 @@ def _declare(lib):
     lib.msda_error_string.argtypes = [i]
     lib.msda_set_tiled_mode.restype = i
     lib.msda_set_tiled_mode.argtypes = [i]
+    lib.msda_set_hybrid_split.restype = i
+    lib.msda_set_hybrid_split.argtypes = [i]
     lib.msda_last_launch_count.restype = i
     lib.msda_last_launch_count.argtypes = []
     lib.msda_forward.restype = i

@@ -110,6 +110,7 @@ struct LevelMeta {
   int dirRows;               // directly accumulated pixel rows per image
   int bktOff[kMaxLevels];    // bucketed levels: first row of the level among one image's bucketed pixel rows
   int bktRows;               // bucketed pixel rows per image (dirRows + bktRows = S)
+  uint32_t sortMask;         // hybrid backward: levels whose grad_value comes from the sorting kernel (one copy each)
 };
 
 __device__ __forceinline__ void load_level_meta(LevelMeta& meta, const int64_t* __restrict__ shapes,
@@ -140,18 +141,30 @@ __device__ __forceinline__ void load_level_meta(LevelMeta& meta, const int64_t* 
 // coarse levels.
 // ---------------------------------------------------------------------------------------------------
 __host__ __device__ inline long long accum_rows_bound(int S, int L, int Lq, int P, int depth) {
+  depth &= 0xffff;                       // see accum_depth_of
+  if (depth < 1) depth = 1;
   const long long per_level = (static_cast<long long>(Lq) * P + depth - 1) / depth;
   return static_cast<long long>(L) * (per_level + 1) + 2ll * S;
 }
 
+// Hybrid backward (dense call site): `depth_and_split` carries, above the 16 bits of the bucket depth, a threshold on the
+// expected adds per element.  Levels above it (coarse levels: hundreds of corner rows per pixel) get their grad_value from
+// msda_bwd_scatter_tiled_kernel, which pre-reduces inside the SM and therefore needs a single copy; levels at or below it
+// (fine levels: little to pre-reduce) keep the direct reductions of msda_bwd_vec_kernel and their buckets.  0 = no split.
+__host__ __device__ inline int accum_depth_of(int depth_and_split) { return depth_and_split & 0xffff; }
+__host__ __device__ inline int accum_split_of(int depth_and_split) { return (depth_and_split >> 16) & 0x7fff; }
+
 // call after load_level_meta (thread 0 fills, then a barrier)
-__device__ __forceinline__ void build_accum_layout(LevelMeta& meta, int L, int Lq, int P, int depth, bool sparse_direct) {
+__device__ __forceinline__ void build_accum_layout(LevelMeta& meta, int L, int Lq, int P, int depth_and_split, bool sparse_direct) {
   if (threadIdx.x == 0) {
+    const int depth = accum_depth_of(depth_and_split), split = accum_split_of(depth_and_split);
     int base = 0, dir = 0, bkt = 0;
+    uint32_t sorted = 0u;
     for (int l = 0; l < L; ++l) {
       const long long hw = static_cast<long long>(meta.H[l]) * meta.W[l];
       const long long adds = hw > 0 ? (static_cast<long long>(Lq) * P + hw - 1) / hw : 1;
-      const int K = static_cast<int>((adds + depth - 1) / depth);
+      int K = static_cast<int>((adds + depth - 1) / depth);
+      if (split > 0 && adds > split && l < 32) { K = 1; sorted |= 1u << l; }
       const bool direct = sparse_direct && hw > 0 && kSparseFactor * Lq * P <= hw;
       meta.accK[l] = direct ? 0 : (K < 1 ? 1 : K);
       meta.accBase[l] = base;
@@ -163,6 +176,7 @@ __device__ __forceinline__ void build_accum_layout(LevelMeta& meta, int L, int L
     meta.accStride = base;
     meta.dirRows = dir;
     meta.bktRows = bkt;
+    meta.sortMask = sorted;
   }
   __syncthreads();
 }

@@ -392,7 +392,9 @@ __device__ __forceinline__ float f16_accum_scale(const uint32_t* __restrict__ ct
 // SPARSE  : GV16 only; some level may be sparse (4*Lq*P <= H_l*W_l <= S, decided on the host from Lq, P, S) and then
 //           adds straight into grad_value (build_accum_layout).  A separate instantiation because the extra
 //           level-uniform branch and addressing in the reduction loop cost the dense encoder shapes ~8 %.
-template <typename T, int D, bool GV16, bool FUSED, typename AT, bool SPARSE>
+// HYB     : GV16 only; hybrid backward of the dense call site: levels in meta.sortMask (see build_accum_layout) get their
+//           grad_value from msda_bwd_scatter_tiled_kernel, this kernel skips their reductions (and does everything else)
+template <typename T, int D, bool GV16, bool FUSED, typename AT, bool SPARSE, bool HYB = false>
 __global__ void __launch_bounds__(kThreads, BWD_MIN_CTAS)
 msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const AT* __restrict__ loc,
@@ -483,6 +485,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
   T* gvd_base = nullptr;                  // sparse levels: this lane's channels of image b in grad_value itself
   size_t acc_row = 0;                     // first accumulator row of (this query's bucket of) the current level
   bool direct = false;                    // current level is sparse: add straight into grad_value (warp-uniform)
+  bool red_here = true;                   // HYB: this kernel reduces the current level's grad_value (warp-uniform)
   float gv_unscale = 1.f;
   if constexpr (GV16) {
     gv16_base = gv16 + (static_cast<size_t>(b) * meta.accStride * M + m) * D + c * VEC;
@@ -491,6 +494,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
       direct = meta.accK[0] == 0;
     }
     acc_row = static_cast<size_t>(meta.accBase[0]) + static_cast<size_t>(direct ? 0 : q % meta.accK[0]) * (meta.H[0] * meta.W[0]);
+    if constexpr (HYB) red_here = (meta.sortMask & 1u) == 0u;
     gv_unscale = 1.f / gv_scale;          // exact: power of two
 #pragma unroll
     for (int i = 0; i < VEC; ++i) go_s[i] *= gv_scale;      // exact: power-of-two scale
@@ -523,7 +527,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
         const uint4 u11 = ldg16(vl + static_cast<size_t>(static_cast<uint32_t>(t.i11) * pg));
 
         // ---- grad_value: (corner weight * attn) * grad_out, scattered with packed reductions ----
-        if (active) {
+        if (active && (!HYB || red_here)) {
           const float ah = t.hhm * a, al = t.lhm * a;
           const float w[4] = {ah * t.hwm, ah * t.lwm, al * t.hwm, al * t.lwm};
           const int idx[4] = {t.i00, t.i01, t.i10, t.i11};
@@ -566,6 +570,7 @@ msda_bwd_vec_kernel(const T* __restrict__ value, const int64_t* __restrict__ sha
             lvl_pix = static_cast<size_t>(meta.start[l]);
             if constexpr (GV16) {
               if constexpr (SPARSE) direct = meta.accK[l] == 0;
+              if constexpr (HYB) red_here = ((meta.sortMask >> l) & 1u) == 0u;
               acc_row = static_cast<size_t>(meta.accBase[l]) + static_cast<size_t>(direct ? 0 : q % meta.accK[l]) * (H * W);
             }
           }
@@ -659,8 +664,22 @@ msda_absmax_kernel(const T* __restrict__ x, size_t n8, uint32_t* __restrict__ ct
                    int gate_want) {
   if (gated_off(gate, gate_want)) return;
   float m = 0.f;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // four independent 16-byte loads in flight per thread (one at a time left the pass latency-bound at ~2.6 TB/s)
+  for (; i + 3 * stride < n8; i += 4 * stride) {
+    uint4 u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = __ldg(reinterpret_cast<const uint4*>(x) + i + j * stride);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[8];
+      unpack16<T>(u[j], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m = fmaxf(m, fabsf(f[k]));
+    }
+  }
+  for (; i < n8; i += stride) {
     float f[8];
     unpack16<T>(__ldg(reinterpret_cast<const uint4*>(x) + i), f);
 #pragma unroll
@@ -938,10 +957,12 @@ static size_t f16_scratch_bytes(int N, int S, int M, int D, int Lq, int L, int P
 extern thread_local int g_last_launches;
 extern std::atomic<long long> g_total_launches;
 extern std::atomic<int> g_tiled_mode;
+extern std::atomic<int> g_hybrid_split;
 #else
 thread_local int g_last_launches = 0;
 std::atomic<long long> g_total_launches{0};
 std::atomic<int> g_tiled_mode{-1};         // msda_set_tiled_mode(); -1 = take MSDA_B200_TILED (default 0) from the environment on first use
+std::atomic<int> g_hybrid_split{8};        // msda_set_hybrid_split(): see build_accum_layout
 #endif
 
 // SM count of the current device (cached per thread; one process drives one GPU)
@@ -955,14 +976,16 @@ static int device_sm_count() {
   return sms;
 }
 
-static bool tiled_enabled() {
+// 0 = direct kernels, 1 = tiled forward + tiled backward (dots + sort), 2 = hybrid backward (direct kernel for the
+// gradients of locations / weights and the fine levels' grad_value, sorting kernel for the coarse levels; direct forward)
+static int tiled_mode() {
   int m = g_tiled_mode.load(std::memory_order_relaxed);
   if (m < 0) {
     const char* e = std::getenv("MSDA_B200_TILED");
-    m = (e && e[0] == '1') ? 1 : 0;          // opt-in: measured slower than the direct kernels so far
+    m = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
     g_tiled_mode.store(m, std::memory_order_relaxed);
   }
-  return m != 0;
+  return m;
 }
 
 // ---- optional per-launch timing of the dominant kernels (bench.py's roofline leg) --------------------
@@ -999,6 +1022,7 @@ struct Problem {
   const float* ref = nullptr;   // fused pre-op: reference points (N, Lq, L, R); nullptr = plain operator
   int R = 0;
   bool aux16 = false;           // fused pre-op only: offsets / logits (and their gradients) are in the 16-bit value type
+  bool hybrid = false;          // hybrid backward: the direct kernel leaves the levels in meta.sortMask to the sorting kernel
   long long vps = 0, gps = 0;   // elements between neighbouring pixels of value / grad_value (0 = dense, M*D)
   // cluster guard: when set, a backward kernel returns at once unless (*gate != 0) == (gate_want != 0)
   const uint32_t* gate = nullptr;
@@ -1106,9 +1130,15 @@ static int launch_fwd_vec(const Problem& pr, const void* value, const int64_t* s
 // ---- tiled kernels (msda_tiled.cuh): dense call site, 16-bit values, head dim 32 ---------------------------
 // What the host can check without reading the shape tensor; everything else (level nesting, halo, window capacity) is
 // decided on the device, where a point that does not fit its window takes the slow path.
-template <typename T> static bool tiled_supported(const Problem& pr) {
+template <typename T> static bool tiled_shape_ok(const Problem& pr) {
   return sizeof(T) == 2 && pr.D == tiled::kD && pr.Lq == pr.S && pr.ref == nullptr && pr.L <= tiled::kMaxL &&
-         pr.L * pr.P <= tiled::kMaxLP && vec_supported<T>(pr) && tiled_enabled();
+         pr.L * pr.P <= tiled::kMaxLP && vec_supported<T>(pr);
+}
+template <typename T> static bool tiled_supported(const Problem& pr) { return tiled_mode() == 1 && tiled_shape_ok<T>(pr); }
+// hybrid backward: dense values / gradients only (the sorting kernel writes the accumulator, not grad_value, so strides
+// would be fine -- but keep the first version to the shape that is measured)
+template <typename T> static bool hybrid_supported(const Problem& pr) {
+  return tiled_mode() == 2 && tiled_shape_ok<T>(pr) && g_hybrid_split.load(std::memory_order_relaxed) > 0;
 }
 
 // persistent grid: one resident wave of the kernel (the two device queries are cached per kernel and thread)
@@ -1146,6 +1176,24 @@ static int launch_fwd_tiled(const Problem& pr, const void* value, const int64_t*
   return static_cast<int>(cudaGetLastError());
 }
 
+// grad_value of all levels (tiled backward) or of the levels in the layout's sortMask (hybrid backward) into the fp16
+// accumulator; ctrl[0] = max|grad_out| must be there already
+template <typename T>
+static int launch_bwd_scatter(const Problem& pr, const int64_t* shapes, const int64_t* lsi, const void* loc, const void* attn,
+                              const void* go, __half* acc16, const uint32_t* ctrl, int depth, cudaStream_t st) {
+  auto kernel = tiled::msda_bwd_scatter_tiled_kernel<T>;
+  const size_t smem = tiled::kScSmemBytes;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const int grid = tiled_grid(kernel, tiled::kScThreads, smem);
+  ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD_SCATTER, st);
+  kernel<<<grid, tiled::kScThreads, smem, st>>>(shapes, lsi, static_cast<const float*>(loc), static_cast<const float*>(attn),
+                                                static_cast<const T*>(go), acc16, ctrl, pr.N, pr.S, pr.M, pr.Lq, pr.L,
+                                                pr.P, depth);
+  ++g_last_launches, ++g_total_launches;
+  return static_cast<int>(cudaGetLastError());
+}
+
 // grad_sampling_loc / grad_attn_weight (+ max|grad_out| into ctrl[0]), then grad_value into the fp16 accumulator
 template <typename T>
 static int launch_bwd_tiled(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
@@ -1166,19 +1214,7 @@ static int launch_bwd_tiled(const Problem& pr, const void* value, const int64_t*
     e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  {
-    auto kernel = tiled::msda_bwd_scatter_tiled_kernel<T>;
-    const size_t smem = tiled::kScSmemBytes;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return static_cast<int>(e);
-    const int grid = tiled_grid(kernel, tiled::kScThreads, smem);
-    ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD_SCATTER, st);
-    kernel<<<grid, tiled::kScThreads, smem, st>>>(shapes, lsi, static_cast<const float*>(loc), static_cast<const float*>(attn),
-                                                  static_cast<const T*>(go), acc16, ctrl, pr.N, pr.S, pr.M, pr.Lq, pr.L,
-                                                  pr.P, depth);
-    ++g_last_launches, ++g_total_launches;
-    return static_cast<int>(cudaGetLastError());
-  }
+  return launch_bwd_scatter<T>(pr, shapes, lsi, loc, attn, go, acc16, ctrl, depth, st);
 }
 
 template <typename T>
@@ -1233,6 +1269,9 @@ static int launch_bwd_vec_impl(const Problem& pr, const void* value, const int64
         ++g_last_launches, ++g_total_launches;
         return static_cast<int>(cudaGetLastError());
       };
+      if constexpr (D == tiled::kD && !FUSED && std::is_same<AT, float>::value) {
+        if (pr.hybrid) return launch16(msda_bwd_vec_kernel<T, D, true, false, float, false, true>);
+      }
       return gv_direct ? launch16(msda_bwd_vec_kernel<T, D, true, FUSED, AT, true>)
                        : launch16(msda_bwd_vec_kernel<T, D, true, FUSED, AT, false>);
     }
@@ -1352,9 +1391,11 @@ static int run_bwd_f16_accum(const Problem& pr, const void* value, const int64_t
   // tiled kernels: one reduction per (destination row, tile) reaches the accumulator -- at most a few hundred adds per
   // element on the coarsest level of a pyramid -- so a single copy per level (no buckets) keeps the fp16 error at ~2e-3
   const bool tiled = tiled_supported<T>(pr) && pr.gate == nullptr;
-  const int depth = tiled ? 0xffff : accum_depth(flags);
+  const bool hybrid = !tiled && hybrid_supported<T>(pr) && pr.gate == nullptr;
+  const int depth = tiled ? 0xffff
+                          : accum_depth(flags) | (hybrid ? std::min(g_hybrid_split.load(std::memory_order_relaxed), 0x7fff) << 16 : 0);
   // a level can only be sparse (4*Lq*P <= H_l*W_l) if 4*Lq*P <= S: decided here, the levels themselves on the device
-  const bool sparse_direct = !(flags & MSDA_BWD_NO_SPARSE_DIRECT) && kSparseFactor * pr.Lq * pr.P <= pr.S;
+  const bool sparse_direct = !hybrid && !(flags & MSDA_BWD_NO_SPARSE_DIRECT) && kSparseFactor * pr.Lq * pr.P <= pr.S;
   // the control block sits right in front of the accumulator only without the guard's counters in between
   uint4* zero_base = zero_ctrl ? reinterpret_cast<uint4*>(ctrl) : reinterpret_cast<uint4*>(acc16);
   msda_zero_f16_buckets_kernel<<<sms * 8, 256, 0, st>>>(zero_base, zero_ctrl ? kF16CtrlBytes / 16 : 0, shapes, lsi,
@@ -1375,12 +1416,15 @@ static int run_bwd_f16_accum(const Problem& pr, const void* value, const int64_t
     e = cudaGetLastError();
     if (e != cudaSuccess) return static_cast<int>(e);
     void* gvd = sparse_direct ? gv : nullptr;                      // sparse levels add straight into grad_value
+    Problem prh = pr;
+    prh.hybrid = hybrid;
     switch (pr.D) {
-      case 16: rc = launch_bwd_vec<T, 16>(pr, value, shapes, lsi, loc, attn, go, nullptr, acc16, gvd, gstride, ctrl, gloc, gattn, true, depth, st); break;
-      case 32: rc = launch_bwd_vec<T, 32>(pr, value, shapes, lsi, loc, attn, go, nullptr, acc16, gvd, gstride, ctrl, gloc, gattn, true, depth, st); break;
-      case 64: rc = launch_bwd_vec<T, 64>(pr, value, shapes, lsi, loc, attn, go, nullptr, acc16, gvd, gstride, ctrl, gloc, gattn, true, depth, st); break;
-      default: rc = launch_bwd_vec<T, 128>(pr, value, shapes, lsi, loc, attn, go, nullptr, acc16, gvd, gstride, ctrl, gloc, gattn, true, depth, st); break;
+      case 16: rc = launch_bwd_vec<T, 16>(prh, value, shapes, lsi, loc, attn, go, nullptr, acc16, gvd, gstride, ctrl, gloc, gattn, true, depth, st); break;
+      case 32: rc = launch_bwd_vec<T, 32>(prh, value, shapes, lsi, loc, attn, go, nullptr, acc16, gvd, gstride, ctrl, gloc, gattn, true, depth, st); break;
+      case 64: rc = launch_bwd_vec<T, 64>(prh, value, shapes, lsi, loc, attn, go, nullptr, acc16, gvd, gstride, ctrl, gloc, gattn, true, depth, st); break;
+      default: rc = launch_bwd_vec<T, 128>(prh, value, shapes, lsi, loc, attn, go, nullptr, acc16, gvd, gstride, ctrl, gloc, gattn, true, depth, st); break;
     }
+    if (rc == 0 && hybrid) rc = launch_bwd_scatter<T>(pr, shapes, lsi, loc, attn, go, acc16, ctrl, depth, st);
   }
   if (rc != 0) return rc;
   const size_t n8_img = static_cast<size_t>(pr.S) * pr.M * pr.D / 8;
@@ -1412,7 +1456,7 @@ MSDA_LAUNCHER int launch_bwd(const Problem& pr_in, const void* value, const int6
     uint32_t* ctrl = static_cast<uint32_t*>(scratch);
     char* payload = static_cast<char*>(scratch) + sl.payload_off;
     // the density pass reads sampling locations: the fused pre-op (raw offsets) and the tiled kernels go unguarded
-    const bool guard = sl.guard && pr.ref == nullptr && !tiled_supported<T>(pr);
+    const bool guard = sl.guard && pr.ref == nullptr && !tiled_supported<T>(pr) && !hybrid_supported<T>(pr);
     if (!guard) {
       if (sl.counters_bytes != 0) {       // the accumulator does not follow the control block directly: clear it separately
         const cudaError_t e0 = cudaMemsetAsync(scratch, 0, kF16CtrlBytes, st);
@@ -1528,8 +1572,14 @@ extern "C" const char* msda_error_string(int code) {
 }
 
 extern "C" int msda_set_tiled_mode(int mode) {
-  const int prev = tiled_enabled() ? 1 : 0;
-  g_tiled_mode.store(mode != 0 ? 1 : 0);
+  const int prev = tiled_mode();
+  g_tiled_mode.store(mode < 0 || mode > 2 ? 0 : mode);
+  return prev;
+}
+
+extern "C" int msda_set_hybrid_split(int adds) {
+  const int prev = g_hybrid_split.load();
+  g_hybrid_split.store(adds < 0 ? 0 : adds);
   return prev;
 }
 

@@ -796,14 +796,14 @@ struct ScLevel {
   uint32_t acc_row0;
   float Hf, Wf;
 };
-__device__ __forceinline__ ScLevel sc_level(const Geom& g, const LevelMeta& meta, int l0, int lv, int tile) {
+__device__ __forceinline__ ScLevel sc_level(const Geom& g, const LevelMeta& meta, const int* lst, int lv, int tile) {
   ScLevel s;
-  s.l = l0 + lv;
+  s.l = lst[lv];
   s.H = g.H[s.l]; s.W = g.W[s.l];
   s.Hf = static_cast<float>(s.H); s.Wf = static_cast<float>(s.W);
   s.wx0 = g.wx0[s.l]; s.wy0 = g.wy0[s.l]; s.wdx = g.wdx[s.l]; s.wdy = g.wdy[s.l];
   s.lbase = 0;
-  for (int k = 0; k < lv; ++k) s.lbase += g.wdx[l0 + k] * g.wdy[l0 + k];
+  for (int k = 0; k < lv; ++k) s.lbase += g.wdx[lst[k]] * g.wdy[lst[k]];
   const int K = meta.accK[s.l];
   s.acc_row0 = static_cast<uint32_t>(meta.accBase[s.l]) + static_cast<uint32_t>(K > 1 ? tile % K : 0) * static_cast<uint32_t>(s.H * s.W);
   return s;
@@ -842,6 +842,7 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
   __shared__ LevelMeta meta;
   __shared__ uint32_t s_warp_tot[kScThreads / 32];
   __shared__ uint32_t s_total, s_nbins;
+  __shared__ int s_lv[kMaxL], s_nlv;         // the levels this kernel handles: all, or meta.sortMask of a hybrid backward
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned char* s_go = smem_raw;
   uint2* s_ent = reinterpret_cast<uint2*>(smem_raw + static_cast<size_t>(kScQueries) * 2 * kRowBytes);
@@ -855,8 +856,15 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
 
   load_level_meta(meta, shapes, lsi, L);
   build_accum_layout(meta, L, Lq, P, depth, false);
-  if (tid == 0) geom_init(g, shapes, lsi, L, kWinRowsCap);
+  if (tid == 0) {
+    geom_init(g, shapes, lsi, L, kWinRowsCap);
+    int n = 0;
+    for (int l = 0; l < L; ++l)
+      if (accum_split_of(depth) == 0 || ((meta.sortMask >> l) & 1u)) s_lv[n++] = l;
+    s_nlv = n;
+  }
   __syncthreads();
+  const int nlv = s_nlv;
   const float gv_scale = f16_accum_scale(ctrl, Lq);
   const int tiles = g.tiles_x * g.tiles_y;
   const long long total = static_cast<long long>(N) * tiles * M;
@@ -900,13 +908,14 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
         *reinterpret_cast<uint4*>(s_go + static_cast<size_t>(qi) * 2 * kRowBytes + kRowBytes + ch * 16) = u;
       }
 
-      for (int l0 = 0; l0 < L; l0 += kScLG) {
-        const int lg = min(kScLG, L - l0);                  // levels of this round
+      for (int i0 = 0; i0 < nlv; i0 += kScLG) {
+        const int lg = min(kScLG, nlv - i0);                // levels of this round
+        const int* lst = s_lv + i0;
         const int ppq = P * lg;                             // point slots per query
         const int npts = nqr * ppq;
         // first window row (bin) of every level of the round, and the round's bin count
         int nrows = 0;
-        for (int lv = 0; lv < lg; ++lv) nrows += g.wdx[l0 + lv] * g.wdy[l0 + lv];
+        for (int lv = 0; lv < lg; ++lv) nrows += g.wdx[lst[lv]] * g.wdy[lst[lv]];
         __syncthreads();                    // previous round's entries / counters / order are no longer read; go rows are staged
         for (int i = tid; i <= nrows; i += kScThreads) s_cnt[i] = 0u;
         if (tid < kScClasses) s_hist[tid] = 0u;
@@ -919,7 +928,7 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
         // keep the level's constants in registers
         const bool fixed = (kScThreads % ppq) == 0;
         const int remF = tid % ppq, qiF = tid / ppq, qstep = kScThreads / ppq;
-        ScLevel sl = sc_level(g, meta, l0, static_cast<int>(static_cast<uint32_t>(remF) / static_cast<uint32_t>(P)), tile);
+        ScLevel sl = sc_level(g, meta, lst, static_cast<int>(static_cast<uint32_t>(remF) / static_cast<uint32_t>(P)), tile);
         const int pF = remF - (remF / P) * P;
 #pragma unroll
         for (int it = 0; it < kScIters; ++it) {
@@ -934,7 +943,7 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
             const int rem = slot - qi * ppq;
             const int lv = static_cast<int>(static_cast<uint32_t>(rem) / static_cast<uint32_t>(P));
             p = rem - lv * P;
-            sl = sc_level(g, meta, l0, lv, tile);
+            sl = sc_level(g, meta, lst, lv, tile);
           }
           if (qi >= nqr) continue;
           const int q = s_qid[qi];
@@ -992,8 +1001,8 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
           if (r0 < r1) {
             // (level, window cell) of bin r0, then walk
             int lv = 0, rr = r0;
-            while (lv + 1 < lg && rr >= g.wdx[l0 + lv] * g.wdy[l0 + lv]) { rr -= g.wdx[l0 + lv] * g.wdy[l0 + lv]; ++lv; }
-            int l = l0 + lv;
+            while (lv + 1 < lg && rr >= g.wdx[lst[lv]] * g.wdy[lst[lv]]) { rr -= g.wdx[lst[lv]] * g.wdy[lst[lv]]; ++lv; }
+            int l = lst[lv];
             int wdx = g.wdx[l];
             int wyr = static_cast<int>(static_cast<uint32_t>(rr) / static_cast<uint32_t>(wdx)), wxr = rr - wyr * wdx;
             for (int r = r0; r < r1; ++r) {
@@ -1013,7 +1022,7 @@ msda_bwd_scatter_tiled_kernel(const int64_t* __restrict__ shapes, const int64_t*
               }
               if (++wxr == wdx) {
                 wxr = 0;
-                if (++wyr == g.wdy[l]) { wyr = 0; ++lv; l = l0 + (lv < lg ? lv : lg - 1); wdx = g.wdx[l]; }
+                if (++wyr == g.wdy[l]) { wyr = 0; ++lv; l = lst[lv < lg ? lv : lg - 1]; wdx = g.wdx[l]; }
               }
             }
           }
