@@ -1092,8 +1092,40 @@ static size_t vec_smem_bytes(int L, int P, bool fused = false, bool bwd = false)
          sizeof(float);
 }
 
+// L1 / shared-memory split of the gather kernels.  Left alone, the driver configured 102 KB of shared memory for the
+// backward (3 CTAs x 16 KB needed: ncu launch__shared_mem_config_size), i.e. 126 KB of L1 for a kernel whose gather misses
+// each cost a cycle of the SM's crossbar request port -- the unit it saturates.  Ask for just what
+// `ctas` resident CTAs need (a hint: the driver rounds up to the next configuration).  MSDA_B200_CARVEOUT=<percent>
+// overrides, -1 keeps the driver's choice.
+static int carveout_percent(size_t dyn_bytes, int ctas) {
+  static const int forced = [] {
+    const char* e = std::getenv("MSDA_B200_CARVEOUT");
+    return e ? std::atoi(e) : -2;
+  }();
+  if (forced >= -1) return forced;
+  const size_t need = static_cast<size_t>(ctas) * (dyn_bytes + 2048);      // + static LevelMeta + the driver's 1 KB per CTA
+  const int pct = static_cast<int>((need * 100 + 233471) / 233472);
+  return pct > 100 ? 100 : pct;
+}
+
 template <typename K>
-static cudaError_t allow_smem(K kernel, size_t bytes) {
+static cudaError_t allow_smem(K kernel, size_t bytes, int ctas = 0) {
+  if (ctas > 0) {
+    struct Entry { const void* fn; int pct; };
+    static thread_local Entry cache[32];
+    static thread_local int cached = 0;
+    const int pct = carveout_percent(bytes, ctas);
+    const void* key = reinterpret_cast<const void*>(kernel);
+    Entry* slot = nullptr;
+    for (int i = 0; i < cached && slot == nullptr; ++i)
+      if (cache[i].fn == key) slot = &cache[i];
+    if (slot == nullptr && cached < 32) { slot = &cache[cached++]; *slot = Entry{key, -1000}; }
+    if ((slot == nullptr || slot->pct != pct) && pct >= 0) {        // set once per kernel (and again if the need changes)
+      const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      if (e != cudaSuccess) return e;
+    }
+    if (slot != nullptr) slot->pct = pct;
+  }
   // the kernels also hold a static LevelMeta (< 1 KB): opt in as soon as dynamic + static could pass the 48 KB default
   if (bytes + 1024 <= 48 * 1024) return cudaSuccess;
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
@@ -1107,7 +1139,7 @@ static int launch_fwd_vec_impl(const Problem& pr, const void* value, const int64
   const int grid = (pr.total_pairs + per_cta - 1) / per_cta;
   const size_t smem = vec_smem_bytes<T, D>(pr.L, pr.P, FUSED, false);
   if (smem > kVecSmemLimit) return MSDA_ERR_BAD_SHAPE;       // not reached: vec_supported() sends such shapes elsewhere
-  cudaError_t e = allow_smem(msda_fwd_vec_kernel<T, D, FUSED, AT>, smem);
+  cudaError_t e = allow_smem(msda_fwd_vec_kernel<T, D, FUSED, AT>, smem, FUSED ? 5 : 6);
   if (e != cudaSuccess) return static_cast<int>(e);
   ScopedKernelTimer timer(MSDA_KERNEL_FORWARD, st);
   msda_fwd_vec_kernel<T, D, FUSED, AT><<<grid, kThreads, smem, st>>>(
@@ -1258,7 +1290,7 @@ static int launch_bwd_vec_impl(const Problem& pr, const void* value, const int64
   if constexpr (sizeof(T) == 2) {
     if (use16) {
       auto launch16 = [&](auto kernel) -> int {
-        cudaError_t err = allow_smem(kernel, smem);
+        cudaError_t err = allow_smem(kernel, smem, BWD_MIN_CTAS);
         if (err != cudaSuccess) return static_cast<int>(err);
         ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD, st);
         kernel<<<grid, kThreads, smem, st>>>(
@@ -1276,7 +1308,7 @@ static int launch_bwd_vec_impl(const Problem& pr, const void* value, const int64
                        : launch16(msda_bwd_vec_kernel<T, D, true, FUSED, AT, false>);
     }
   }
-  e = allow_smem(msda_bwd_vec_kernel<T, D, false, FUSED, AT, false>, smem);
+  e = allow_smem(msda_bwd_vec_kernel<T, D, false, FUSED, AT, false>, smem, BWD_MIN_CTAS);
   if (e != cudaSuccess) return static_cast<int>(e);
   ScopedKernelTimer timer(MSDA_KERNEL_BACKWARD, st);
   msda_bwd_vec_kernel<T, D, false, FUSED, AT, false><<<grid, kThreads, smem, st>>>(
