@@ -193,3 +193,30 @@ def test_decoder_reference_points_input():
     assert pts.shape == (2, 5, 3, 2) and torch.allclose(pts[0, 0, 1], boxes[0, 0, :2] * torch.tensor([0.5, 0.75]))
     with pytest.raises(ValueError):
         W.decoder_reference_points_input(torch.rand(1, 2, 3), vr[:1])
+
+
+def test_torch_extension_is_built_and_mirrors_the_ctypes_route(built_library):
+    """csrc/torch_binding.cpp: the compiled torch extension over the same C ABI loads next to the library, exposes upstream's
+    two functions and refuses CPU / non-contiguous tensors with upstream's messages -- before any CUDA call."""
+    from vision_instance_seg_b200 import MultiScaleDeformableAttention as MSDA
+    ext = _lib.torch_extension()
+    assert ext is not None, "torch extension not built: __graft_entry__.build() compiles it with g++"
+    assert ext.abi_version() == pkg.load_library().msda_abi_version()
+    value = torch.zeros(1, 4, 1, 4)
+    shapes = torch.tensor([[2, 2]])
+    lsi = torch.zeros(1, dtype=torch.long)
+    loc = torch.zeros(1, 1, 1, 1, 1, 2)
+    attn = torch.zeros(1, 1, 1, 1, 1)
+    for route in ("extension", "ctypes"):
+        saved = _lib._torch_ext
+        if route == "ctypes":
+            _lib._torch_ext = None
+        try:
+            with pytest.raises(RuntimeError, match="value must be a CUDA tensor"):
+                MSDA.ms_deform_attn_forward(value, shapes, lsi, loc, attn, 64)
+            with pytest.raises(RuntimeError, match="value tensor has to be contiguous"):
+                MSDA.ms_deform_attn_forward(value.transpose(1, 3), shapes, lsi, loc, attn, 64)
+            with pytest.raises(RuntimeError, match="grad_output must be a CUDA tensor|value must be a CUDA tensor"):
+                MSDA.ms_deform_attn_backward(value, shapes, lsi, loc, attn, torch.zeros(1, 1, 4), 64)
+        finally:
+            _lib._torch_ext = saved

@@ -59,6 +59,10 @@ def _meta(t: torch.Tensor, device) -> torch.Tensor:
 
 
 def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+    ext = _lib.torch_extension()
+    if ext is not None:        # compiled torch extension over the same C ABI (same checks, same errors, less host time)
+        return ext.ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                          int(im2col_step))
     for t, n in ((value, "value"), (spatial_shapes, "spatial_shapes"), (level_start_index, "level_start_index"),
                  (sampling_loc, "sampling_loc"), (attn_weight, "attn_weight")):
         _require(t, n)
@@ -84,6 +88,10 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
 
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
                             im2col_step):
+    ext = _lib.torch_extension()
+    if ext is not None:
+        return ext.ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                           grad_output, int(im2col_step), int(backward_flags))
     for t, n in ((value, "value"), (spatial_shapes, "spatial_shapes"), (level_start_index, "level_start_index"),
                  (sampling_loc, "sampling_loc"), (attn_weight, "attn_weight"), (grad_output, "grad_output")):
         _require(t, n)

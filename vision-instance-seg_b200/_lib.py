@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_NAME = "libmsda_b200.so"
-_lock = threading.Lock()
+_lock = threading.RLock()
 _lib = None
 
 MSDA_F32, MSDA_F64, MSDA_BF16, MSDA_F16 = 0, 1, 2, 3
@@ -137,6 +137,37 @@ def load_library():
                     "(nvcc, sm_100a). This operator has no CPU or PyTorch fallback.")
             _lib = _declare(ctypes.CDLL(path))
     return _lib
+
+
+_torch_ext = None
+_torch_ext_tried = False
+
+
+def torch_extension():
+    """The compiled torch extension over the same C ABI (csrc/torch_binding.cpp -> _msda_torch*.so next to the library;
+    built by ``__graft_entry__.build()``), or None: not built, switched off with MSDA_B200_NO_TORCH_EXT=1, or the library
+    path is overridden (the extension links the in-tree library).  Callers fall back to the ctypes route, which reaches
+    the very same entry points -- there is no other implementation behind either."""
+    global _torch_ext, _torch_ext_tried
+    if _torch_ext_tried:
+        return _torch_ext
+    with _lock:
+        if not _torch_ext_tried:
+            ext = None
+            if os.environ.get("MSDA_B200_NO_TORCH_EXT") != "1" and "MSDA_B200_LIBRARY" not in os.environ \
+                    and os.path.exists(library_path()):
+                try:
+                    import importlib
+                    import torch  # noqa: F401  (its shared libraries must be loaded first)
+                    want = load_library().msda_abi_version()
+                    ext = importlib.import_module(__package__ + "._msda_torch")
+                    if ext.abi_version() != want:
+                        ext = None
+                except ImportError:
+                    ext = None
+            _torch_ext = ext
+            _torch_ext_tried = True
+    return _torch_ext
 
 
 def check(rc: int, what: str) -> None:
