@@ -709,21 +709,46 @@ msda_zero_f16_buckets_kernel(uint4* __restrict__ scratch, size_t ctrl_vecs, cons
   const size_t nthr = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = tid; i < total; i += nthr) scratch[i] = z;
   if (meta.dirRows > 0) {
-    const size_t per_img = static_cast<size_t>(meta.dirRows) * vpp;
-    const size_t dtotal = static_cast<size_t>(N) * per_img;
-    for (size_t i = tid; i < dtotal; i += nthr) {
-      const size_t b = i / per_img, j = i - b * per_img;
-      const int r = static_cast<int>(j / vpp), v = static_cast<int>(j - static_cast<size_t>(r) * vpp);
-      int l = 0;                                                     // sparse level that owns direct row r
-      for (int k = 0; k < L; ++k)
-        if (meta.accK[k] == 0 && r >= meta.dirOff[k]) l = k;
-      const size_t pix = b * S + meta.start[l] + (r - meta.dirOff[l]);
-      *reinterpret_cast<uint4*>(gv + pix * gps + v * 8) = z;
+    // a sparse level's rows are one contiguous range per image: level by level, (image, vector) flattened, with 32-bit
+    // index arithmetic whenever it fits (the 64-bit divisions of a row-by-row walk made this pass instruction-bound:
+    // 47 us for the 167 MB of the 300-query decoder shape)
+    const bool dense = static_cast<size_t>(gps) == static_cast<size_t>(M) * D;
+    for (int l = 0; l < L; ++l) {
+      if (meta.accK[l] != 0) continue;
+      const size_t n16 = static_cast<size_t>(meta.H[l]) * meta.W[l] * vpp;         // vectors of the level in one image
+      const size_t ltotal = static_cast<size_t>(N) * n16;
+      uint16_t* lvl = gv + static_cast<size_t>(meta.start[l]) * gps;
+      const size_t img_elems = static_cast<size_t>(S) * gps;
+      if (ltotal < (1ull << 32)) {
+        const uint32_t n16u = static_cast<uint32_t>(n16), vppu = static_cast<uint32_t>(vpp);
+        for (size_t i = tid; i < ltotal; i += nthr) {
+          const uint32_t iu = static_cast<uint32_t>(i), b = iu / n16u, j = iu - b * n16u;
+          uint16_t* img = lvl + b * img_elems;
+          if (dense) {
+            reinterpret_cast<uint4*>(img)[j] = z;
+          } else {
+            const uint32_t r = j / vppu, v = j - r * vppu;
+            *reinterpret_cast<uint4*>(img + static_cast<size_t>(r) * gps + v * 8) = z;
+          }
+        }
+      } else {
+        for (size_t i = tid; i < ltotal; i += nthr) {
+          const size_t b = i / n16, j = i - b * n16, r = j / vpp, v = j - r * vpp;
+          *reinterpret_cast<uint4*>(lvl + b * img_elems + r * gps + v * 8) = z;
+        }
+      }
     }
   }
 }
 
-// bucketed, scaled fp16 accumulation buffer -> 16-bit grad_value: sum the K_l copies in fp32, unscale, round once
+// bucketed, scaled fp16 accumulation buffer -> 16-bit grad_value: sum the K_l copies in fp32, unscale, round once.
+// blockIdx.y = image; one flattened index over the 16-byte vectors of the image's bucketed rows (a sparse level's
+// grad_value rows already hold their sums), so every thread gets the same share whatever the levels' sizes; the
+// level of a vector is found by comparing against the levels' first indices, its constants come from a small shared
+// table (the first version spent ~160 instructions per vector on divisions, the per-element level search and 64-bit
+// index arithmetic: issue-bound at 0.09 ms for the cfg3 shape, 0.03 ms for the few rows of the decoder shape).
+// 32-bit index arithmetic: S * M * D * 4 bytes < 2^32 for the vector kernels, and the accumulator of one image holds
+// fewer vectors than that.
 template <typename T>
 __global__ void __launch_bounds__(256)
 msda_round_f16_buckets_kernel(const __half* __restrict__ acc, T* __restrict__ dst, const int64_t* __restrict__ shapes,
@@ -732,36 +757,70 @@ msda_round_f16_buckets_kernel(const __half* __restrict__ acc, T* __restrict__ ds
                               const uint32_t* __restrict__ gate, int gate_want) {
   if (gated_off(gate, gate_want)) return;
   __shared__ LevelMeta meta;
+  struct LevelRow { uint32_t first, K, kstride, src0, drow0; };   // first flattened vector, copies, vectors per copy, ...
+  __shared__ LevelRow tab[kMaxLevels];
+  __shared__ int s_nlv;
   load_level_meta(meta, shapes, lsi, L);
   build_accum_layout(meta, L, Lq, P, depth, sparse_direct != 0);
-  const float inv = 1.f / f16_accum_scale(ctrl, Lq);        // exact: power of two
-  const uint32_t vec_per_pix = static_cast<uint32_t>(M * D / 8);
-  // blockIdx.y = image; only the bucketed levels' rows are visited (a sparse level's grad_value rows already hold
-  // their sums); 32-bit index arithmetic (S * M * D * 4 bytes < 2^32 for the vector kernels)
-  const uint32_t per_img = static_cast<uint32_t>(meta.bktRows) * vec_per_pix;
-  for (int b = blockIdx.y; b < N; b += gridDim.y)
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per_img; i += gridDim.x * blockDim.x) {
-    const int r = static_cast<int>(i / vec_per_pix);                 // row among the image's bucketed rows
-    const int v = static_cast<int>(i - static_cast<uint32_t>(r) * vec_per_pix);
-    int l = 0;
-    for (int k = 0; k < L; ++k)
-      if (meta.accK[k] != 0 && r >= meta.bktOff[k]) l = k;
-    const int s = meta.start[l] + (r - meta.bktOff[l]);
-    const size_t pix = static_cast<size_t>(b) * S + s;
-    const int hw = meta.H[l] * meta.W[l];
-    const size_t row0 = static_cast<size_t>(b) * meta.accStride + meta.accBase[l] + (s - meta.start[l]);
-    float sum[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) sum[k] = 0.f;
-    for (int k = 0; k < meta.accK[l]; ++k) {
-      float f[8];
-      unpack16<__half>(__ldcs(reinterpret_cast<const uint4*>(acc) + (row0 + static_cast<size_t>(k) * hw) * vec_per_pix + v), f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sum[j] += f[j];
+  const uint32_t vpp = static_cast<uint32_t>(M * D / 8);
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int l = 0; l < L; ++l) {
+      if (meta.accK[l] == 0) continue;
+      LevelRow t;
+      t.first = static_cast<uint32_t>(meta.bktOff[l]) * vpp;
+      t.K = static_cast<uint32_t>(meta.accK[l]);
+      t.kstride = static_cast<uint32_t>(meta.H[l] * meta.W[l]) * vpp;
+      t.src0 = static_cast<uint32_t>(meta.accBase[l]) * vpp - t.first;      // + i: vector of copy 0 inside the image's accumulator
+      t.drow0 = static_cast<uint32_t>(meta.start[l] - meta.bktOff[l]);      // + row among the bucketed rows: pixel row in the image
+      tab[n++] = t;
     }
+    s_nlv = n;
+  }
+  __syncthreads();
+  const int nlv = s_nlv;
+  const float inv = 1.f / f16_accum_scale(ctrl, Lq);        // exact: power of two
+  const uint32_t per_img = static_cast<uint32_t>(meta.bktRows) * vpp;
+  const bool dense = static_cast<uint32_t>(gps) == vpp * 8u;
+  for (int b = blockIdx.y; b < N; b += gridDim.y) {
+    const uint4* src_img = reinterpret_cast<const uint4*>(acc) + static_cast<size_t>(b) * meta.accStride * vpp;
+    T* dst_img = dst + static_cast<size_t>(b) * S * gps;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per_img; i += gridDim.x * blockDim.x) {
+      int li = 0;
+      for (int k = 1; k < nlv; ++k) li += (i >= tab[k].first) ? 1 : 0;          // levels are in ascending order of `first`
+      const LevelRow t = tab[li];
+      const uint4* src = src_img + (t.src0 + i);
+      float sum[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sum[j] *= inv;
-    *reinterpret_cast<uint4*>(dst + pix * gps + v * 8) = pack16<T>(sum);
+      for (int j = 0; j < 8; ++j) sum[j] = 0.f;
+      uint32_t k = 0;
+      for (; k + 4 <= t.K; k += 4) {                                             // coarse levels: 4 loads in flight
+        uint4 u[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) u[q] = __ldcs(src + static_cast<size_t>(k + q) * t.kstride);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float f[8];
+          unpack16<__half>(u[q], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sum[j] += f[j];
+        }
+      }
+      for (; k < t.K; ++k) {
+        float f[8];
+        unpack16<__half>(__ldcs(src + static_cast<size_t>(k) * t.kstride), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum[j] += f[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum[j] *= inv;
+      if (dense) {
+        reinterpret_cast<uint4*>(dst_img)[t.drow0 * vpp + i] = pack16<T>(sum);
+      } else {
+        const uint32_t r = i / vpp, v = i - r * vpp;
+        *reinterpret_cast<uint4*>(dst_img + static_cast<size_t>(t.drow0 + r) * gps + v * 8) = pack16<T>(sum);
+      }
+    }
   }
 }
 

@@ -122,4 +122,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ms_deform_attn_forward", &forward, "ms_deform_attn_forward");
   m.def("ms_deform_attn_backward", &backward, "ms_deform_attn_backward (flags: include/msda_b200.h MSDA_BWD_*)");
   m.def("abi_version", []() { return msda_abi_version(); });
+  m.def("raise_for_code", [](int code) { check(code, "raise_for_code"); },
+        "turn a C-ABI return code into the RuntimeError the two functions raise (0: no error); used by the CPU tests");
 }
