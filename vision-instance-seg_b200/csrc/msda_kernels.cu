@@ -372,7 +372,8 @@ __device__ __forceinline__ void group_reduce_scatter(float (&v)[G][R], int c) {
 // sum_p attn*bilinear <= Lq * max|grad_out| for ANY input (attention weights of a query sum to <= 1 in the
 // module; bilinear weights to <= 1), so with scale = the largest power of two such that
 // Lq * max|grad_out| * scale <= 2^15 no partial sum can overflow fp16 (max 65504), whatever the sampling
-// pattern.  ctrl[0] holds the bits of max|grad_out| (written by msda_absmax_kernel).
+// pattern.  ctrl[0] holds the bits of max|grad_out| (bits of a non-negative float order like unsigned integers: atomicMax
+// in msda_zero_f16_buckets_kernel, or in the tiled backward's dots kernel).
 __device__ __forceinline__ float f16_accum_scale(const uint32_t* __restrict__ ctrl, int Lq) {
   const float bound = __uint_as_float(__ldg(ctrl)) * static_cast<float>(Lq);
   if (!(bound > 0.f)) return 1.f;
@@ -657,47 +658,19 @@ msda_zero_fill_kernel(uint4* __restrict__ p, size_t n16, const uint32_t* __restr
     p[i] = z;
 }
 
-// max |x| over a 16-bit tensor -> ctrl[0] (bits of a non-negative float order like unsigned integers)
-template <typename T>
-__global__ void __launch_bounds__(256)
-msda_absmax_kernel(const T* __restrict__ x, size_t n8, uint32_t* __restrict__ ctrl, const uint32_t* __restrict__ gate,
-                   int gate_want) {
-  if (gated_off(gate, gate_want)) return;
-  float m = 0.f;
-  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  // four independent 16-byte loads in flight per thread (one at a time left the pass latency-bound at ~2.6 TB/s)
-  for (; i + 3 * stride < n8; i += 4 * stride) {
-    uint4 u[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) u[j] = __ldg(reinterpret_cast<const uint4*>(x) + i + j * stride);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float f[8];
-      unpack16<T>(u[j], f);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) m = fmaxf(m, fabsf(f[k]));
-    }
-  }
-  for (; i < n8; i += stride) {
-    float f[8];
-    unpack16<T>(__ldg(reinterpret_cast<const uint4*>(x) + i), f);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) m = fmaxf(m, fabsf(f[k]));
-  }
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(ctrl, __float_as_uint(m));
-}
-
 // zero the control block, the rows of the bucketed fp16 accumulator that the device-side layout actually uses
 // (the host only knows the upper bound accum_rows_bound(); for few queries the layout is ~half of it) and, when
 // `gv` is given, the grad_value rows of the sparse levels, which receive their reductions directly
-// (16-bit element types only: 8 elements per 16-byte vector; gps = elements between neighbouring pixels of gv)
-static __global__ void __launch_bounds__(256)
+// (16-bit element types only: 8 elements per 16-byte vector; gps = elements between neighbouring pixels of gv).
+// When `go` is given the same launch also reduces max|grad_out| into *go_max (which the caller has zeroed with a memset,
+// so ctrl_vecs is 0 then): the reads of the one pass overlap the writes of the other, one launch and ~25 us less per
+// backward than two kernels back to back.
+template <typename T>
+__global__ void __launch_bounds__(256)
 msda_zero_f16_buckets_kernel(uint4* __restrict__ scratch, size_t ctrl_vecs, const int64_t* __restrict__ shapes,
                              const int64_t* __restrict__ lsi, uint16_t* __restrict__ gv, int N, int S, int M, int D,
-                             int Lq, int L, int P, int depth, int gps, const uint32_t* __restrict__ gate, int gate_want) {
+                             int Lq, int L, int P, int depth, int gps, const T* __restrict__ go, size_t go_n8,
+                             uint32_t* __restrict__ go_max, const uint32_t* __restrict__ gate, int gate_want) {
   if (gated_off(gate, gate_want)) return;
   __shared__ LevelMeta meta;
   load_level_meta(meta, shapes, lsi, L);
@@ -707,7 +680,45 @@ msda_zero_f16_buckets_kernel(uint4* __restrict__ scratch, size_t ctrl_vecs, cons
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthr = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t i = tid; i < total; i += nthr) scratch[i] = z;
+  if (go != nullptr) {
+    // interleaved: every round issues four independent 16-byte loads of grad_out, then this thread's share of the zero
+    // stores while they are in flight, then folds the loads into the running maximum
+    float m = 0.f;
+    const size_t nl = (go_n8 + nthr - 1) / nthr;                     // load rounds of this thread
+    const size_t ns = (total + nthr - 1) / nthr;                     // store rounds
+    const size_t rounds = (nl + 3) / 4;
+    const size_t spr = rounds ? (ns + rounds - 1) / rounds : ns;     // stores per round of four loads
+    size_t ks = 0;
+    for (size_t kl = 0; kl < nl; kl += 4) {
+      uint4 u[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const size_t idx = tid + (kl + j) * nthr;
+        u[j] = idx < go_n8 ? __ldg(reinterpret_cast<const uint4*>(go) + idx) : z;
+      }
+      const size_t ks_end = ks + spr < ns ? ks + spr : ns;
+      for (; ks < ks_end; ++ks) {
+        const size_t idx = tid + ks * nthr;
+        if (idx < total) scratch[idx] = z;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f[8];
+        unpack16<T>(u[j], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m = fmaxf(m, fabsf(f[k]));
+      }
+    }
+    for (; ks < ns; ++ks) {
+      const size_t idx = tid + ks * nthr;
+      if (idx < total) scratch[idx] = z;
+    }
+#pragma unroll
+    for (int sft = 16; sft >= 1; sft >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sft));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(go_max, __float_as_uint(m));
+  } else {
+    for (size_t i = tid; i < total; i += nthr) scratch[i] = z;
+  }
   if (meta.dirRows > 0) {
     // a sparse level's rows are one contiguous range per image: level by level, (image, vector) flattened, with 32-bit
     // index arithmetic whenever it fits (the 64-bit divisions of a row-by-row walk made this pass instruction-bound:
@@ -1472,7 +1483,7 @@ static int run_bwd_fp32_accum(const Problem& pr, const void* value, const int64_
   return static_cast<int>(cudaGetLastError());
 }
 
-// 16-bit values, scaled fp16 buckets (+ sparse levels added directly): zero, max|grad_out|, backward, sum + round.
+// 16-bit values, scaled fp16 buckets (+ sparse levels added directly): zero + max|grad_out| (one launch), backward, sum + round.
 template <typename T>
 static int run_bwd_f16_accum(const Problem& pr, const void* value, const int64_t* shapes, const int64_t* lsi,
                              const void* loc, const void* attn, const void* go, void* gv, void* gloc, void* gattn,
@@ -1487,25 +1498,30 @@ static int run_bwd_f16_accum(const Problem& pr, const void* value, const int64_t
                           : accum_depth(flags) | (hybrid ? std::min(g_hybrid_split.load(std::memory_order_relaxed), 0x7fff) << 16 : 0);
   // a level can only be sparse (4*Lq*P <= H_l*W_l) if 4*Lq*P <= S: decided here, the levels themselves on the device
   const bool sparse_direct = !hybrid && !(flags & MSDA_BWD_NO_SPARSE_DIRECT) && kSparseFactor * pr.Lq * pr.P <= pr.S;
-  // the control block sits right in front of the accumulator only without the guard's counters in between
+  // Direct kernels: the zero pass also reduces max|grad_out| into ctrl[0], which must then be clear before the launch
+  // (a memset node; the kernel cannot order its own clearing against other CTAs' atomicMax).  Tiled kernels: the dots
+  // kernel produces the maximum, the zero pass clears the control block itself when it sits right in front of the
+  // accumulator (i.e. without the guard's counters in between).
+  cudaError_t e = cudaSuccess;
+  if (!tiled && zero_ctrl) {
+    e = cudaMemsetAsync(ctrl, 0, kF16CtrlBytes, st);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    zero_ctrl = false;
+  }
+  const size_t go_n8 = static_cast<size_t>(pr.N) * pr.Lq * pr.M * pr.D / 8;     // D is a multiple of 16 here
   uint4* zero_base = zero_ctrl ? reinterpret_cast<uint4*>(ctrl) : reinterpret_cast<uint4*>(acc16);
-  msda_zero_f16_buckets_kernel<<<sms * 8, 256, 0, st>>>(zero_base, zero_ctrl ? kF16CtrlBytes / 16 : 0, shapes, lsi,
-                                                       sparse_direct ? static_cast<uint16_t*>(gv) : nullptr,
-                                                       pr.N, pr.S, pr.M, pr.D, pr.Lq, pr.L, pr.P, depth, gstride,
-                                                       pr.gate, pr.gate_want);
+  msda_zero_f16_buckets_kernel<T><<<sms * 8, 256, 0, st>>>(zero_base, zero_ctrl ? kF16CtrlBytes / 16 : 0, shapes, lsi,
+                                                          sparse_direct ? static_cast<uint16_t*>(gv) : nullptr,
+                                                          pr.N, pr.S, pr.M, pr.D, pr.Lq, pr.L, pr.P, depth, gstride,
+                                                          tiled ? nullptr : static_cast<const T*>(go), go_n8, ctrl,
+                                                          pr.gate, pr.gate_want);
   ++g_last_launches, ++g_total_launches;
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   int rc;
   if (tiled) {
     rc = launch_bwd_tiled<T>(pr, value, shapes, lsi, loc, attn, go, acc16, ctrl, gloc, gattn, depth, st);
   } else {
-    const size_t n8 = static_cast<size_t>(pr.N) * pr.Lq * pr.M * pr.D / 8;     // D is a multiple of 16 here
-    const int grid = static_cast<int>(std::min<size_t>((n8 + 255) / 256, static_cast<size_t>(sms) * 8));
-    msda_absmax_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(go), n8, ctrl, pr.gate, pr.gate_want);
-    ++g_last_launches, ++g_total_launches;
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return static_cast<int>(e);
     void* gvd = sparse_direct ? gv : nullptr;                      // sparse levels add straight into grad_value
     Problem prh = pr;
     prh.hybrid = hybrid;
