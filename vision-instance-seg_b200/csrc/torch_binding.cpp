@@ -119,8 +119,11 @@ std::vector<at::Tensor> backward(const at::Tensor& value, const at::Tensor& spat
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "torch extension over the C ABI of libmsda_b200.so (B200 multi-scale deformable attention)";
-  m.def("ms_deform_attn_forward", &forward, "ms_deform_attn_forward");
-  m.def("ms_deform_attn_backward", &backward, "ms_deform_attn_backward (flags: include/msda_b200.h MSDA_BWD_*)");
+  // no Python object is touched inside: run without the GIL, like the ctypes route does (a launch that blocks on a full
+  // queue must not stall autograd's other thread or the bench's clock sampler)
+  m.def("ms_deform_attn_forward", &forward, "ms_deform_attn_forward", pybind11::call_guard<pybind11::gil_scoped_release>());
+  m.def("ms_deform_attn_backward", &backward, "ms_deform_attn_backward (flags: include/msda_b200.h MSDA_BWD_*)",
+        pybind11::call_guard<pybind11::gil_scoped_release>());
   m.def("abi_version", []() { return msda_abi_version(); });
   m.def("raise_for_code", [](int code) { check(code, "raise_for_code"); },
         "turn a C-ABI return code into the RuntimeError the two functions raise (0: no error); used by the CPU tests");
