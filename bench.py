@@ -296,7 +296,8 @@ def secondary_rows(args, cfg, batch, dev, lib):
       cold  : 256 MiB written between calls (L2 flushed);  warm: the same inputs back to back (value of one image batch
               does not fit the 126 MB L2 at this size, so `warm` mostly keeps loc / attn / the accumulator tail);
       fp32  : the same geometry with float32 values;       uniform: sampling locations U(-0.05, 1.05) (no locality);
-      tiled : the opt-in tiled kernels (msda_set_tiled_mode(1)) on the encoder-like inputs."""
+      tiled : the opt-in tiled kernels (msda_set_tiled_mode(1)) on the encoder-like inputs;
+      hybrid: mode 2 (direct forward; backward = direct kernel for the fine levels + sorting kernel for the two coarsest)."""
     import torch
     from vision_instance_seg_b200 import MultiScaleDeformableAttention as MSDA, workloads as W
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -315,16 +316,19 @@ def secondary_rows(args, cfg, batch, dev, lib):
                 ts.append(e0.elapsed_time(e1))
         return statistics.median(ts)
 
-    def row(dtype, kind, tiled=False, cold=True):
+    def row(dtype, kind, tiled=0, cold=True):
         maker = W.make_uniform_inputs if kind == "uniform" else W.make_encoder_inputs
         v, ss, lsi, loc, attn = maker(cfg["shapes"], batch, dtype, seed=777, device=dev)
         go = torch.randn(batch, loc.shape[1], v.shape[2] * v.shape[3], device=dev).to(dtype)
-        prev = lib.msda_set_tiled_mode(1 if tiled else 0)
+        prev = lib.msda_set_tiled_mode(int(tiled))
+        prev_split = lib.msda_set_hybrid_split(30) if int(tiled) == 2 else None
         try:
             f = timed(lambda: MSDA.ms_deform_attn_forward(v, ss, lsi, loc, attn, 128), cold)
             b = timed(lambda: MSDA.ms_deform_attn_backward(v, ss, lsi, loc, attn, go, 128), cold)
         finally:
             lib.msda_set_tiled_mode(prev)
+            if prev_split is not None:
+                lib.msda_set_hybrid_split(prev_split)
         pts = loc.numel() // 2
         return {"forward_ms": f, "backward_ms": b, "points_per_s": pts / ((f + b) * 1e-3)}
 
@@ -334,7 +338,8 @@ def secondary_rows(args, cfg, batch, dev, lib):
            "uniform_locations": row(dtype, "uniform")}
     if dtype != torch.float32:
         out["fp32_values"] = row(torch.float32, "encoder")
-        out["tiled_kernels"] = row(dtype, "encoder", tiled=True)
+        out["tiled_kernels"] = row(dtype, "encoder", tiled=1)
+        out["hybrid_backward"] = row(dtype, "encoder", tiled=2)
     del flush
     torch.cuda.empty_cache()
     return out
